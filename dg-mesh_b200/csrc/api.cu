@@ -1,0 +1,198 @@
+// api.cu -- the C-ABI of libdgmesh_b200.so (see include/dgmesh_b200.h).
+#include "../../include/dgmesh_b200.h"
+#include "common.cuh"
+#include "raster_kernels.h"
+
+#include <string.h>
+
+namespace {
+thread_local char g_last_error[256] = "";
+int check(cudaError_t e) {
+  if (e == cudaSuccess) return DGM_OK;
+  strncpy(g_last_error, cudaGetErrorString(e), sizeof(g_last_error) - 1);
+  return DGM_E_LAUNCH;
+}
+int bad(const char* msg) {
+  strncpy(g_last_error, msg, sizeof(g_last_error) - 1);
+  return DGM_E_BADARG;
+}
+}  // namespace
+
+namespace dgm {
+Profiler g_prof;
+// ---- state export (parity tests): rebuild the reference-visible views from the
+// private workspaces.  point_list_keys is reconstructed as (tile << 32 | depth bits),
+// the key the reference sorts on (rasterizer_impl.cu:98-106).
+__global__ void export_keys_kernel(int T, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                   const float* __restrict__ depths, uint64_t* __restrict__ keys) {
+  const int t = blockIdx.x;
+  if (t >= T) return;
+  const uint2 r = ranges[t];
+  for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x)
+    keys[i] = ((uint64_t)t << 32) | (uint64_t)__float_as_uint(depths[point_list[i]]);
+}
+
+cudaError_t launch_export_state(int P, int W, int H, int64_t R_cap, const void* geom_ws, const void* binning_ws,
+                                const void* img_ws, float* depths, float* means2D, float* cov3D, float* conic_opacity,
+                                float* rgb, uint32_t* tiles_touched, uint8_t* clamped, uint64_t* point_list_keys,
+                                uint32_t* point_list, uint32_t* ranges, float* final_T, uint32_t* n_contrib,
+                                cudaStream_t s) {
+  const unsigned gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  const int T = gx * gy;
+  const size_t npix = (size_t)W * H;
+  GeomWS g = GeomWS::from((char*)geom_ws, P);
+  ImgWS im = ImgWS::from((char*)img_ws, npix, T);
+  BinWS b = BinWS::from((char*)binning_ws, (size_t)R_cap);
+  const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+  if (depths) cudaMemcpyAsync(depths, g.depths, sizeof(float) * P, k, s);
+  if (means2D) cudaMemcpyAsync(means2D, g.means2D, sizeof(float2) * P, k, s);
+  if (cov3D) cudaMemcpyAsync(cov3D, g.cov3D, sizeof(float) * 6 * P, k, s);
+  if (conic_opacity) cudaMemcpyAsync(conic_opacity, g.conic_opacity, sizeof(float4) * P, k, s);
+  if (rgb) cudaMemcpyAsync(rgb, g.rgb, sizeof(float) * 3 * P, k, s);
+  if (tiles_touched) cudaMemcpyAsync(tiles_touched, g.tiles_touched, sizeof(uint32_t) * P, k, s);
+  if (clamped) cudaMemcpyAsync(clamped, g.clamped, 3 * (size_t)P, k, s);
+  if (ranges) cudaMemcpyAsync(ranges, im.ranges, sizeof(uint2) * T, k, s);
+  if (final_T) cudaMemcpyAsync(final_T, im.final_T, sizeof(float) * npix, k, s);
+  if (n_contrib) cudaMemcpyAsync(n_contrib, im.n_contrib, sizeof(uint32_t) * npix, k, s);
+  // the caller sizes point_list / keys by the R it read from the status block (R <= R_cap)
+  if (point_list_keys) export_keys_kernel<<<T, 128, 0, s>>>(T, im.ranges, b.point_list, g.depths, point_list_keys);
+  if (point_list) {
+    // copy only the populated prefix: R is the end of the last non-empty range; copy R_cap is safe too
+    cudaMemcpyAsync(point_list, b.point_list, sizeof(uint32_t) * (size_t)R_cap, k, s);
+  }
+  return cudaGetLastError();
+}
+}  // namespace dgm
+
+extern "C" {
+
+const char* dgm_version(void) { return "dgmesh_b200 0.1 sm_100a"; }
+const char* dgm_last_error(void) { return g_last_error; }
+
+int dgr_workspace_sizes(int P, int W, int H, int64_t R_cap, size_t* geom_bytes, size_t* binning_bytes,
+                        size_t* img_bytes) {
+  if (P < 0 || W <= 0 || H <= 0 || R_cap < 0) return bad("dgr_workspace_sizes: negative size");
+  const unsigned gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  size_t gb, bb, ib;
+  dgm::GeomWS::from(nullptr, (size_t)P, &gb);
+  dgm::BinWS::from(nullptr, (size_t)R_cap, &bb);
+  dgm::ImgWS::from(nullptr, (size_t)W * H, (size_t)gx * gy, &ib);
+  if (geom_bytes) *geom_bytes = gb;
+  if (binning_bytes) *binning_bytes = bb;
+  if (img_bytes) *img_bytes = ib;
+  return DGM_OK;
+}
+
+int dgr_forward(int P, int D, int M, const float* background, int W, int H, const float* means3D, const float* shs,
+                const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, float* out_color, int* radii,
+                void* geom_ws, size_t geom_bytes, void* binning_ws, size_t binning_bytes, int64_t R_cap, void* img_ws,
+                size_t img_bytes, int32_t* status, void* stream) {
+  if (P < 0 || W <= 0 || H <= 0 || R_cap < 0) return bad("dgr_forward: negative size");
+  if (!background || !viewmatrix || !projmatrix || !cam_pos || !out_color || !status)
+    return bad("dgr_forward: null required pointer");
+  if (P > 0) {
+    if (!means3D || !opacities) return bad("dgr_forward: means3D / opacities missing");
+    if ((shs == nullptr) == (colors_precomp == nullptr)) return bad("dgr_forward: exactly one of shs / colors_precomp");
+    if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+      return bad("dgr_forward: exactly one of scales+rotations / cov3D_precomp");
+    if (shs && (M <= 0 || M > 16 || (D + 1) * (D + 1) > M || D < 0 || D > 3))
+      return bad("dgr_forward: SH degree / coefficient count");
+  }
+  if (P == 0) {
+    // the reference skips the whole pipeline and returns the zero-initialised image
+    // (rasterize_points.cu:64,80: torch::full(0.0) and `if (P != 0)`)
+    cudaMemsetAsync(out_color, 0, sizeof(float) * 3 * (size_t)W * H, (cudaStream_t)stream);
+    cudaMemsetAsync(status, 0, sizeof(int32_t) * DGR_STATUS_WORDS, (cudaStream_t)stream);
+    return check(cudaGetLastError());
+  }
+  size_t gb, bb, ib;
+  dgr_workspace_sizes(P, W, H, R_cap, &gb, &bb, &ib);
+  if (geom_bytes < gb || binning_bytes < bb || img_bytes < ib || !geom_ws || !binning_ws || !img_ws) {
+    strncpy(g_last_error, "dgr_forward: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  dgm::FwdArgs a;
+  a.P = P; a.D = D; a.M = M; a.background = background; a.W = W; a.H = H;
+  a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
+  a.scales = scales; a.scale_modifier = scale_modifier; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+  a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+  a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.prefiltered = prefiltered;
+  a.out_color = out_color; a.radii = radii;
+  a.geom_ws = geom_ws; a.binning_ws = binning_ws; a.img_ws = img_ws; a.R_cap = R_cap; a.status = status;
+  return check(dgm::launch_forward(a, (cudaStream_t)stream));
+}
+
+int dgr_backward(int P, int D, int M, const float* background, int W, int H, const float* means3D, const float* shs,
+                 const float* colors_precomp, const float* scales, float scale_modifier, const float* rotations,
+                 const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                 float tan_fovx, float tan_fovy, const int* radii, void* geom_ws, void* binning_ws, int64_t R_cap,
+                 void* img_ws, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                 float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+                 float* dL_drot, void* stream) {
+  if (P < 0 || W <= 0 || H <= 0 || R_cap < 0) return bad("dgr_backward: negative size");
+  if (P == 0) return DGM_OK;
+  if (!background || !means3D || !viewmatrix || !projmatrix || !cam_pos || !geom_ws || !binning_ws || !img_ws ||
+      !dL_dpix || !dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale ||
+      !dL_drot)
+    return bad("dgr_backward: null required pointer");
+  if (shs && !dL_dsh) return bad("dgr_backward: dL_dsh missing");
+  dgm::BwdArgs a;
+  a.P = P; a.D = D; a.M = M; a.background = background; a.W = W; a.H = H;
+  a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales;
+  a.scale_modifier = scale_modifier; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+  a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+  a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.radii = radii;
+  a.geom_ws = geom_ws; a.binning_ws = binning_ws; a.img_ws = img_ws; a.R_cap = R_cap;
+  a.dL_dpix = dL_dpix; a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity;
+  a.dL_dcolor = dL_dcolor; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh;
+  a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+  return check(dgm::launch_backward(a, (cudaStream_t)stream));
+}
+
+int dgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                     void* stream) {
+  if (P < 0) return bad("dgr_mark_visible: negative size");
+  if (P > 0 && (!means3D || !viewmatrix || !projmatrix || !present)) return bad("dgr_mark_visible: null pointer");
+  return check(dgm::launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream));
+}
+
+int dgr_export_state(int P, int W, int H, int64_t R_cap, const void* geom_ws, const void* binning_ws,
+                     const void* img_ws, float* depths, float* means2D, float* cov3D, float* conic_opacity, float* rgb,
+                     uint32_t* tiles_touched, uint8_t* clamped, uint64_t* point_list_keys, uint32_t* point_list,
+                     uint32_t* ranges, float* final_T, uint32_t* n_contrib, void* stream) {
+  if (P < 0 || W <= 0 || H <= 0 || R_cap < 0 || !geom_ws || !binning_ws || !img_ws)
+    return bad("dgr_export_state: bad argument");
+  return check(dgm::launch_export_state(P, W, H, R_cap, geom_ws, binning_ws, img_ws, depths, means2D, cov3D,
+                                        conic_opacity, rgb, tiles_touched, clamped, point_list_keys, point_list,
+                                        ranges, final_T, n_contrib, (cudaStream_t)stream));
+}
+
+int dgm_profile_enable(int on) {
+  using dgm::g_prof;
+  if (on && !g_prof.ev[0][0]) {
+    for (int k = 0; k < DGM_K_COUNT; ++k)
+      for (int j = 0; j < 2; ++j)
+        if (cudaEventCreate(&g_prof.ev[k][j]) != cudaSuccess) return check(cudaGetLastError());
+  }
+  g_prof.on = on != 0;
+  for (int k = 0; k < DGM_K_COUNT; ++k) g_prof.used[k] = false;
+  return DGM_OK;
+}
+
+int dgm_profile_read(float* ms_host, int n) {
+  using dgm::g_prof;
+  if (!ms_host || n < 0) return bad("dgm_profile_read: bad argument");
+  for (int k = 0; k < n && k < DGM_K_COUNT; ++k) {
+    ms_host[k] = -1.f;
+    if (!g_prof.used[k]) continue;
+    if (cudaEventSynchronize(g_prof.ev[k][1]) != cudaSuccess) return check(cudaGetLastError());
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, g_prof.ev[k][0], g_prof.ev[k][1]) != cudaSuccess) return check(cudaGetLastError());
+    ms_host[k] = ms;
+  }
+  return DGM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,564 @@
+// raster_bwd.cu -- backward pass of the tile-based 3D-Gaussian rasterizer for sm_100a.
+//
+//   render_bwd_kernel      gradient of the alpha-composite (role of renderCUDA,
+//                          dgr/cuda_rasterizer/backward.cu:399-557)
+//   preprocess_bwd_kernel  chain rule to means3D / scales / rotations / SH / opacity
+//                          (computeCov2DCUDA + preprocessCUDA, backward.cu:144-396, fused)
+//
+// The reference issues 9 global float atomics per contributing (pixel, Gaussian)
+// pair.  Here each warp (8x4 pixels) reduces its 32 partial gradients with a
+// transposing butterfly (14 shuffles for 9 values), adds the 9 sums into a per-tile
+// shared-memory accumulator, and the tile flushes once per (tile, Gaussian) with
+// vector reductions (red.global.add.v4.f32) into a [P,12] accumulator that the fused
+// preprocess-backward consumes and re-zeroes.  The per-pair arithmetic follows the
+// reference's back-to-front recurrence; only the summation order differs (the
+// reference's own order is non-deterministic).
+#include "common.cuh"
+#include "raster_math.cuh"
+#include "raster_kernels.h"
+
+namespace dgm {
+
+#define RB 256
+#define ACC_STRIDE 9
+
+// Reduce 9 per-lane values over the warp.  On return lane (4*k) holds the total of
+// v[k] for k = 0..7 in `r8`, and every lane holds the total of v[8] in `r9`.
+__device__ __forceinline__ void warp_reduce9(const float (&v)[9], unsigned lane, float& r8, float& r9) {
+  const unsigned FULL = 0xffffffffu;
+  float a[4];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float send = up ? v[k] : v[k + 4];
+      const float keep = up ? v[k + 4] : v[k];
+      a[k] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+  }
+  float b[2];
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float send = up ? a[k] : a[k + 2];
+      const float keep = up ? a[k + 2] : a[k];
+      b[k] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+  }
+  float c;
+  {
+    const bool up = lane & 4;
+    const float send = up ? b[0] : b[1];
+    const float keep = up ? b[1] : b[0];
+    c = keep + __shfl_xor_sync(FULL, send, 4);
+  }
+  c += __shfl_xor_sync(FULL, c, 2);
+  c += __shfl_xor_sync(FULL, c, 1);
+  r8 = c;  // value index = (bit4 ? 4 : 0) + (bit3 ? 2 : 0) + (bit2 ? 1 : 0)
+  float d = v[8];
+  d += __shfl_xor_sync(FULL, d, 16);
+  d += __shfl_xor_sync(FULL, d, 8);
+  d += __shfl_xor_sync(FULL, d, 4);
+  d += __shfl_xor_sync(FULL, d, 2);
+  d += __shfl_xor_sync(FULL, d, 1);
+  r9 = d;
+}
+
+__global__ void __launch_bounds__(256) render_bwd_kernel(
+    const uint2* __restrict__ ranges, const float4* __restrict__ inst_geo, const float4* __restrict__ inst_attr,
+    int W, int H, const float* __restrict__ bg_color, const float* __restrict__ final_Ts,
+    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels, float4* __restrict__ grad_acc) {
+  __shared__ __align__(128) float4 s_geo[2][RB];
+  __shared__ __align__(128) float4 s_attr[2][2 * RB];
+  __shared__ float s_acc[RB * ACC_STRIDE];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ int s_maxc;
+
+  const unsigned gx = (W + TILE_X - 1) / TILE_X;
+  const unsigned tile = blockIdx.x;
+  const unsigned tx = tile % gx, ty = tile / gx;
+  const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int wx0 = tx * TILE_X + (wid & 1) * 8, wy0 = ty * TILE_Y + (wid >> 1) * 4;
+  const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const uint32_t pix_id = W * py + px;
+  const float pixfx = (float)px, pixfy = (float)py;
+  const float bx0 = (float)wx0, bx1 = (float)(wx0 + 7), by0 = (float)wy0, by1 = (float)(wy0 + 3);
+
+  const uint2 range = ranges[tile];
+  const int total = range.y - range.x;
+  if (total == 0) return;  // uniform per CTA
+
+  const float T_final = inside ? final_Ts[pix_id] : 0;
+  float T = T_final;
+  const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+
+  if (tid == 0) {
+    s_maxc = 0;
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < RB * ACC_STRIDE; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  // positions >= max over the warp / tile of n_contrib can be skipped altogether
+  int wmax = last_contributor;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (lane == 0) atomicMax(&s_maxc, wmax);
+  __syncthreads();
+  const int maxc = min(s_maxc, total);
+  const int rounds = (maxc + RB - 1) / RB;
+  if (rounds == 0) return;
+
+  // batch i covers positions [hi_i - cnt_i, hi_i), hi_0 = maxc, walking towards the front
+  if (tid == 0) {
+    const int hi = maxc, lo = max(0, hi - RB);
+    const uint32_t cnt = hi - lo;
+    mbar_expect_tx(&s_bar[0], cnt * 48u);
+    tma_load_1d(&s_geo[0][0], inst_geo + range.x + lo, cnt * 16u, &s_bar[0]);
+    tma_load_1d(&s_attr[0][0], inst_attr + 2 * ((size_t)range.x + lo), cnt * 32u, &s_bar[0]);
+  }
+
+  float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
+  if (inside) {
+    const size_t HW = (size_t)H * W;
+    dLp0 = dL_dpixels[0 * HW + pix_id];
+    dLp1 = dL_dpixels[1 * HW + pix_id];
+    dLp2 = dL_dpixels[2 * HW + pix_id];
+  }
+  float bg_dot_dpixel = 0;
+  bg_dot_dpixel += bg_color[0] * dLp0;
+  bg_dot_dpixel += bg_color[1] * dLp1;
+  bg_dot_dpixel += bg_color[2] * dLp2;
+
+  float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
+  float last_alpha = 0.f;
+  float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
+  // d(pixel coordinate)/d(NDC), backward.cu:457-458 (double literal 0.5)
+  const float ddelx_dx = 0.5 * W;
+  const float ddely_dy = 0.5 * H;
+
+  for (int i = 0; i < rounds; ++i) {
+    const int st = i & 1;
+    const int hi = maxc - i * RB, lo = max(0, hi - RB);
+    const int cnt = hi - lo;
+    mbar_wait(&s_bar[st], (i >> 1) & 1);
+    __syncthreads();  // previous batch fully flushed; other stage free
+    if (tid == 0 && i + 1 < rounds) {
+      const int nhi = lo, nlo = max(0, nhi - RB);
+      const uint32_t ncnt = nhi - nlo;
+      mbar_expect_tx(&s_bar[st ^ 1], ncnt * 48u);
+      tma_load_1d(&s_geo[st ^ 1][0], inst_geo + range.x + nlo, ncnt * 16u, &s_bar[st ^ 1]);
+      tma_load_1d(&s_attr[st ^ 1][0], inst_attr + 2 * ((size_t)range.x + nlo), ncnt * 32u, &s_bar[st ^ 1]);
+    }
+    // ---- cull (same conservative extent test as the forward pass)
+    unsigned keep[RB / 32];
+#pragma unroll
+    for (int k = 0; k < RB / 32; ++k) {
+      const int r = k * 32 + lane;
+      bool kp = false;
+      if (r < cnt && (lo + r) < wmax) {
+        const float4 ge = s_geo[st][r];
+        const float ddx = fmaxf(fmaxf(bx0 - ge.x, ge.x - bx1), 0.0f);
+        const float ddy = fmaxf(fmaxf(by0 - ge.y, ge.y - by1), 0.0f);
+        kp = !(ddx > ge.z || ddy > ge.w);
+      }
+      keep[k] = __ballot_sync(0xffffffffu, kp);
+    }
+    // ---- back to front
+#pragma unroll
+    for (int k = RB / 32 - 1; k >= 0; --k) {
+      unsigned mask = keep[k];
+      while (mask) {
+        const int bit = 31 - __clz(mask);
+        mask &= ~(1u << bit);
+        const int j = k * 32 + bit;
+        const int pos = lo + j;  // 0-based position in the tile list
+        const float4 ge = s_geo[st][j];
+        const float4 con_o = s_attr[st][2 * j];
+        const float4 col = s_attr[st][2 * j + 1];
+        float v[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) v[q] = 0.f;
+        bool contrib = false;
+        // reference: contributor (1-based) must be <= last_contributor
+        if (pos < last_contributor) {
+          const float dx = ge.x - pixfx, dy = ge.y - pixfy;
+          const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
+          if (!(power > 0.0f)) {
+            const float G = expf(power);
+            const float alpha = min(0.99f, con_o.w * G);
+            if (!(alpha < 1.0f / 255.0f)) {
+              contrib = true;
+              T = T / (1.f - alpha);
+              const float dchannel_dcolor = alpha * T;
+              float dL_dalpha = 0.0f;
+              accum0 = last_alpha * lc0 + (1.f - last_alpha) * accum0;
+              lc0 = col.x;
+              dL_dalpha += (col.x - accum0) * dLp0;
+              v[6] = dchannel_dcolor * dLp0;
+              accum1 = last_alpha * lc1 + (1.f - last_alpha) * accum1;
+              lc1 = col.y;
+              dL_dalpha += (col.y - accum1) * dLp1;
+              v[7] = dchannel_dcolor * dLp1;
+              accum2 = last_alpha * lc2 + (1.f - last_alpha) * accum2;
+              lc2 = col.z;
+              dL_dalpha += (col.z - accum2) * dLp2;
+              v[8] = dchannel_dcolor * dLp2;
+              dL_dalpha *= T;
+              last_alpha = alpha;
+              dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+              const float dL_dG = con_o.w * dL_dalpha;
+              const float gdx = G * dx;
+              const float gdy = G * dy;
+              const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+              const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+              v[0] = dL_dG * dG_ddelx * ddelx_dx;
+              v[1] = dL_dG * dG_ddely * ddely_dy;
+              v[2] = -0.5f * gdx * dx * dL_dG;
+              v[3] = -0.5f * gdx * dy * dL_dG;
+              v[4] = -0.5f * gdy * dy * dL_dG;
+              v[5] = G * dL_dalpha;
+            }
+          }
+        }
+        if (__any_sync(0xffffffffu, contrib)) {
+          float r8, r9;
+          warp_reduce9(v, lane, r8, r9);
+          float* acc = &s_acc[j * ACC_STRIDE];
+          if ((lane & 3) == 0) atomicAdd(&acc[((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)], r8);
+          if (lane == 1) atomicAdd(&acc[8], r9);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- flush this batch: one vector reduction triple per (tile, Gaussian)
+    if ((int)tid < cnt) {
+      float* acc = &s_acc[tid * ACC_STRIDE];
+      float a[9];
+      bool nz = false;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        a[q] = acc[q];
+        nz |= (a[q] != 0.f);
+        acc[q] = 0.f;
+      }
+      if (nz) {
+        const uint32_t id = __float_as_uint(s_attr[st][2 * tid + 1].w);
+        float* dst = reinterpret_cast<float*>(grad_acc + 3 * (size_t)id);
+        red_add_v4(dst, a[0], a[1], a[2], a[3]);
+        red_add_v4(dst + 4, a[4], a[5], a[6], a[7]);
+        atomicAdd(dst + 8, a[8]);
+      }
+    }
+  }
+}
+
+// ===================================================== preprocess (bwd) ====
+// SH colour gradient (backward.cu:20-139): returns dL/d(mean) contribution, writes dL_dsh.
+__device__ __forceinline__ float3 sh_backward(int deg, int M, const float3 pos, const float3 campos,
+                                              const float* __restrict__ sh, const uint8_t* clamped,
+                                              const float3 dL_dcolor, float* __restrict__ dL_dsh) {
+  const float3 dir_orig = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
+  const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+  const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+  float dRGB[3] = {dL_dcolor.x, dL_dcolor.y, dL_dcolor.z};
+  dRGB[0] *= clamped[0] ? 0 : 1;
+  dRGB[1] *= clamped[1] ? 0 : 1;
+  dRGB[2] *= clamped[2] ? 0 : 1;
+  float ddir[3] = {0.f, 0.f, 0.f};  // dL/d(dir) accumulated over channels
+  float w[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w[k] = 0.f;
+  w[0] = kSH0;
+  float xx = 0, yy = 0, zz = 0, xy = 0, yz = 0, xz = 0;
+  if (deg > 0) {
+    w[1] = -kSH1 * y;
+    w[2] = kSH1 * z;
+    w[3] = -kSH1 * x;
+    if (deg > 1) {
+      xx = x * x, yy = y * y, zz = z * z;
+      xy = x * y, yz = y * z, xz = x * z;
+      w[4] = kSH2[0] * xy;
+      w[5] = kSH2[1] * yz;
+      w[6] = kSH2[2] * (2.f * zz - xx - yy);
+      w[7] = kSH2[3] * xz;
+      w[8] = kSH2[4] * (xx - yy);
+      if (deg > 2) {
+        w[9] = kSH3[0] * y * (3.f * xx - yy);
+        w[10] = kSH3[1] * xy * z;
+        w[11] = kSH3[2] * y * (4.f * zz - xx - yy);
+        w[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+        w[13] = kSH3[4] * x * (4.f * zz - xx - yy);
+        w[14] = kSH3[5] * z * (xx - yy);
+        w[15] = kSH3[6] * x * (xx - 3.f * yy);
+      }
+    }
+  }
+  const int ncoef = (deg + 1) * (deg + 1);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (k < M) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) dL_dsh[k * 3 + ch] = (k < ncoef) ? w[k] * dRGB[ch] : 0.f;
+    }
+  }
+
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (deg > 0) {
+      dx = -kSH1 * sh[3 * 3 + ch];
+      dy = -kSH1 * sh[1 * 3 + ch];
+      dz = kSH1 * sh[2 * 3 + ch];
+      if (deg > 1) {
+        dx += kSH2[0] * y * sh[4 * 3 + ch] + kSH2[2] * 2.f * -x * sh[6 * 3 + ch] + kSH2[3] * z * sh[7 * 3 + ch] +
+              kSH2[4] * 2.f * x * sh[8 * 3 + ch];
+        dy += kSH2[0] * x * sh[4 * 3 + ch] + kSH2[1] * z * sh[5 * 3 + ch] + kSH2[2] * 2.f * -y * sh[6 * 3 + ch] +
+              kSH2[4] * 2.f * -y * sh[8 * 3 + ch];
+        dz += kSH2[1] * y * sh[5 * 3 + ch] + kSH2[2] * 2.f * 2.f * z * sh[6 * 3 + ch] + kSH2[3] * x * sh[7 * 3 + ch];
+        if (deg > 2) {
+          dx += (kSH3[0] * sh[9 * 3 + ch] * 3.f * 2.f * xy + kSH3[1] * sh[10 * 3 + ch] * yz +
+                 kSH3[2] * sh[11 * 3 + ch] * -2.f * xy + kSH3[3] * sh[12 * 3 + ch] * -3.f * 2.f * xz +
+                 kSH3[4] * sh[13 * 3 + ch] * (-3.f * xx + 4.f * zz - yy) + kSH3[5] * sh[14 * 3 + ch] * 2.f * xz +
+                 kSH3[6] * sh[15 * 3 + ch] * 3.f * (xx - yy));
+          dy += (kSH3[0] * sh[9 * 3 + ch] * 3.f * (xx - yy) + kSH3[1] * sh[10 * 3 + ch] * xz +
+                 kSH3[2] * sh[11 * 3 + ch] * (-3.f * yy + 4.f * zz - xx) +
+                 kSH3[3] * sh[12 * 3 + ch] * -3.f * 2.f * yz + kSH3[4] * sh[13 * 3 + ch] * -2.f * xy +
+                 kSH3[5] * sh[14 * 3 + ch] * -2.f * yz + kSH3[6] * sh[15 * 3 + ch] * -3.f * 2.f * xy);
+          dz += (kSH3[1] * sh[10 * 3 + ch] * xy + kSH3[2] * sh[11 * 3 + ch] * 4.f * 2.f * yz +
+                 kSH3[3] * sh[12 * 3 + ch] * 3.f * (2.f * zz - xx - yy) +
+                 kSH3[4] * sh[13 * 3 + ch] * 4.f * 2.f * xz + kSH3[5] * sh[14 * 3 + ch] * (xx - yy));
+        }
+      }
+    }
+    ddir[0] += dx * dRGB[ch];
+    ddir[1] += dy * dRGB[ch];
+    ddir[2] += dz * dRGB[ch];
+  }
+  // through the normalisation dir = v / |v| (auxiliary.h:112-122)
+  const float3 vv = dir_orig;
+  const float sum2 = vv.x * vv.x + vv.y * vv.y + vv.z * vv.z;
+  const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+  float3 r;
+  r.x = ((+sum2 - vv.x * vv.x) * ddir[0] - vv.y * vv.x * ddir[1] - vv.z * vv.x * ddir[2]) * invsum32;
+  r.y = (-vv.x * vv.y * ddir[0] + (sum2 - vv.y * vv.y) * ddir[1] - vv.z * vv.y * ddir[2]) * invsum32;
+  r.z = (-vv.x * vv.z * ddir[0] - vv.y * vv.z * ddir[1] + (sum2 - vv.z * vv.z) * ddir[2]) * invsum32;
+  return r;
+}
+
+__global__ void __launch_bounds__(128) preprocess_bwd_kernel(
+    int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
+    const float* __restrict__ shs, const float* __restrict__ scales, const float* __restrict__ rotations,
+    float scale_modifier, const float* __restrict__ cov3D_precomp, const float* __restrict__ view,
+    const float* __restrict__ proj, float focal_x, float focal_y, float tan_fovx, float tan_fovy,
+    const float* __restrict__ cam_pos, GeomWS g, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
+    float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D,
+    float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscale,
+    float* __restrict__ dL_drot) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const bool visible = radii[idx] > 0;
+  // fetch + clear the accumulators written by render_bwd_kernel
+  const float4 a0 = g.grad_acc[3 * idx + 0], a1 = g.grad_acc[3 * idx + 1], a2 = g.grad_acc[3 * idx + 2];
+  g.grad_acc[3 * idx + 0] = make_float4(0, 0, 0, 0);
+  g.grad_acc[3 * idx + 1] = make_float4(0, 0, 0, 0);
+  g.grad_acc[3 * idx + 2] = make_float4(0, 0, 0, 0);
+  const float2 dm2 = make_float2(a0.x, a0.y);
+  const float3 dcon = make_float3(a0.z, a0.w, a1.x);  // (xx, xy, yy) slots .x .y .w of the reference float4
+  const float dop = a1.y;
+  const float3 dcol = make_float3(a1.z, a1.w, a2.x);
+
+  dL_dmean2D[3 * idx + 0] = dm2.x;
+  dL_dmean2D[3 * idx + 1] = dm2.y;
+  dL_dmean2D[3 * idx + 2] = 0.f;
+  dL_dconic[4 * idx + 0] = dcon.x;
+  dL_dconic[4 * idx + 1] = dcon.y;
+  dL_dconic[4 * idx + 2] = 0.f;
+  dL_dconic[4 * idx + 3] = dcon.z;
+  dL_dopacity[idx] = dop;
+  dL_dcolor[3 * idx + 0] = dcol.x;
+  dL_dcolor[3 * idx + 1] = dcol.y;
+  dL_dcolor[3 * idx + 2] = dcol.z;
+
+  float dcov[6] = {0, 0, 0, 0, 0, 0};
+  float3 dmean = make_float3(0, 0, 0);
+  float3 dscale = make_float3(0, 0, 0);
+  float4 drot = make_float4(0, 0, 0, 0);
+
+  if (!visible) {
+    if (dL_dsh)
+      for (int k = 0; k < M * 3; ++k) dL_dsh[(size_t)idx * M * 3 + k] = 0.f;
+  } else {
+    const float3 mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    const float* cov3D = cov3D_precomp ? cov3D_precomp + 6 * idx : g.cov3D + 6 * idx;
+    // ---------------- gradient through the 2D covariance / conic (backward.cu:144-274)
+    EwaFrame fr;
+    ewa_frame(mean, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, view, fr);
+    const float limx = 1.3f * tan_fovx, limy = 1.3f * tan_fovy;
+    const float x_grad_mul = fr.txtz < -limx || fr.txtz > limx ? 0 : 1;
+    const float y_grad_mul = fr.tytz < -limy || fr.tytz > limy ? 0 : 1;
+    const float3 c2 = ewa_cov2d(fr);
+    const float a = c2.x, b = c2.y, c = c2.z;
+    const float denom = a * c - b * b;
+    float dL_da = 0, dL_db = 0, dL_dc = 0;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    const Mat3& T = fr.T;
+    const Mat3& Vrk = fr.Vrk;
+    if (denom2inv != 0) {
+      dL_da = denom2inv * (-c * c * dcon.x + 2 * b * c * dcon.y + (denom - a * c) * dcon.z);
+      dL_dc = denom2inv * (-a * a * dcon.z + 2 * a * b * dcon.y + (denom - a * c) * dcon.x);
+      dL_db = denom2inv * 2 * (b * c * dcon.x - (denom + 2 * b * b) * dcon.y + a * b * dcon.z);
+      dcov[0] = (T.c[0][0] * T.c[0][0] * dL_da + T.c[0][0] * T.c[1][0] * dL_db + T.c[1][0] * T.c[1][0] * dL_dc);
+      dcov[3] = (T.c[0][1] * T.c[0][1] * dL_da + T.c[0][1] * T.c[1][1] * dL_db + T.c[1][1] * T.c[1][1] * dL_dc);
+      dcov[5] = (T.c[0][2] * T.c[0][2] * dL_da + T.c[0][2] * T.c[1][2] * dL_db + T.c[1][2] * T.c[1][2] * dL_dc);
+      dcov[1] = 2 * T.c[0][0] * T.c[0][1] * dL_da + (T.c[0][0] * T.c[1][1] + T.c[0][1] * T.c[1][0]) * dL_db +
+                2 * T.c[1][0] * T.c[1][1] * dL_dc;
+      dcov[2] = 2 * T.c[0][0] * T.c[0][2] * dL_da + (T.c[0][0] * T.c[1][2] + T.c[0][2] * T.c[1][0]) * dL_db +
+                2 * T.c[1][0] * T.c[1][2] * dL_dc;
+      dcov[4] = 2 * T.c[0][2] * T.c[0][1] * dL_da + (T.c[0][1] * T.c[1][2] + T.c[0][2] * T.c[1][1]) * dL_db +
+                2 * T.c[1][1] * T.c[1][2] * dL_dc;
+    }
+    const float dL_dT00 = 2 * (T.c[0][0] * Vrk.c[0][0] + T.c[0][1] * Vrk.c[0][1] + T.c[0][2] * Vrk.c[0][2]) * dL_da +
+                          (T.c[1][0] * Vrk.c[0][0] + T.c[1][1] * Vrk.c[0][1] + T.c[1][2] * Vrk.c[0][2]) * dL_db;
+    const float dL_dT01 = 2 * (T.c[0][0] * Vrk.c[1][0] + T.c[0][1] * Vrk.c[1][1] + T.c[0][2] * Vrk.c[1][2]) * dL_da +
+                          (T.c[1][0] * Vrk.c[1][0] + T.c[1][1] * Vrk.c[1][1] + T.c[1][2] * Vrk.c[1][2]) * dL_db;
+    const float dL_dT02 = 2 * (T.c[0][0] * Vrk.c[2][0] + T.c[0][1] * Vrk.c[2][1] + T.c[0][2] * Vrk.c[2][2]) * dL_da +
+                          (T.c[1][0] * Vrk.c[2][0] + T.c[1][1] * Vrk.c[2][1] + T.c[1][2] * Vrk.c[2][2]) * dL_db;
+    const float dL_dT10 = 2 * (T.c[1][0] * Vrk.c[0][0] + T.c[1][1] * Vrk.c[0][1] + T.c[1][2] * Vrk.c[0][2]) * dL_dc +
+                          (T.c[0][0] * Vrk.c[0][0] + T.c[0][1] * Vrk.c[0][1] + T.c[0][2] * Vrk.c[0][2]) * dL_db;
+    const float dL_dT11 = 2 * (T.c[1][0] * Vrk.c[1][0] + T.c[1][1] * Vrk.c[1][1] + T.c[1][2] * Vrk.c[1][2]) * dL_dc +
+                          (T.c[0][0] * Vrk.c[1][0] + T.c[0][1] * Vrk.c[1][1] + T.c[0][2] * Vrk.c[1][2]) * dL_db;
+    const float dL_dT12 = 2 * (T.c[1][0] * Vrk.c[2][0] + T.c[1][1] * Vrk.c[2][1] + T.c[1][2] * Vrk.c[2][2]) * dL_dc +
+                          (T.c[0][0] * Vrk.c[2][0] + T.c[0][1] * Vrk.c[2][1] + T.c[0][2] * Vrk.c[2][2]) * dL_db;
+    const Mat3& Wm = fr.W;
+    const float dL_dJ00 = Wm.c[0][0] * dL_dT00 + Wm.c[0][1] * dL_dT01 + Wm.c[0][2] * dL_dT02;
+    const float dL_dJ02 = Wm.c[2][0] * dL_dT00 + Wm.c[2][1] * dL_dT01 + Wm.c[2][2] * dL_dT02;
+    const float dL_dJ11 = Wm.c[1][0] * dL_dT10 + Wm.c[1][1] * dL_dT11 + Wm.c[1][2] * dL_dT12;
+    const float dL_dJ12 = Wm.c[2][0] * dL_dT10 + Wm.c[2][1] * dL_dT11 + Wm.c[2][2] * dL_dT12;
+    const float tz = 1.f / fr.t.z;
+    const float tz2 = tz * tz;
+    const float tz3 = tz2 * tz;
+    const float dL_dtx = x_grad_mul * -focal_x * tz2 * dL_dJ02;
+    const float dL_dty = y_grad_mul * -focal_y * tz2 * dL_dJ12;
+    const float dL_dtz = -focal_x * tz2 * dL_dJ00 - focal_y * tz2 * dL_dJ11 + (2 * focal_x * fr.t.x) * tz3 * dL_dJ02 +
+                         (2 * focal_y * fr.t.y) * tz3 * dL_dJ12;
+    dmean = xform_vec4x3_T(make_float3(dL_dtx, dL_dty, dL_dtz), view);
+
+    // ---------------- screen-space mean -> 3D mean (backward.cu:366-381)
+    const float4 m_hom = xform4x4(mean, proj);
+    const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+    const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+    const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+    float3 dm;
+    dm.x = (proj[0] * m_w - proj[3] * mul1) * dm2.x + (proj[1] * m_w - proj[3] * mul2) * dm2.y;
+    dm.y = (proj[4] * m_w - proj[7] * mul1) * dm2.x + (proj[5] * m_w - proj[7] * mul2) * dm2.y;
+    dm.z = (proj[8] * m_w - proj[11] * mul1) * dm2.x + (proj[9] * m_w - proj[11] * mul2) * dm2.y;
+    dmean.x += dm.x;
+    dmean.y += dm.y;
+    dmean.z += dm.z;
+
+    // ---------------- SH colour (backward.cu:20-139, 383-385)
+    if (shs) {
+      const float3 cp = make_float3(cam_pos[0], cam_pos[1], cam_pos[2]);
+      const float3 dms = sh_backward(D, M, mean, cp, shs + (size_t)idx * M * 3, g.clamped + 3 * idx, dcol,
+                                     dL_dsh + (size_t)idx * M * 3);
+      dmean.x += dms.x;
+      dmean.y += dms.y;
+      dmean.z += dms.z;
+    }
+    // ---------------- 3D covariance -> scale / rotation (backward.cu:279-341)
+    if (scales) {
+      const float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
+      const float4 q = make_float4(rotations[4 * idx], rotations[4 * idx + 1], rotations[4 * idx + 2],
+                                   rotations[4 * idx + 3]);
+      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      Mat3 R;
+      quat_to_R(q, R);
+      const float3 s = make_float3(scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z);
+      Mat3 S;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) S.c[i][j] = (i == j) ? 1.0f : 0.0f;
+      S.c[0][0] = s.x;
+      S.c[1][1] = s.y;
+      S.c[2][2] = s.z;
+      const Mat3 Mm = mat3_mul(S, R);
+      Mat3 dSig;
+      dSig.c[0][0] = dcov[0];
+      dSig.c[0][1] = 0.5f * dcov[1];
+      dSig.c[0][2] = 0.5f * dcov[2];
+      dSig.c[1][0] = 0.5f * dcov[1];
+      dSig.c[1][1] = dcov[3];
+      dSig.c[1][2] = 0.5f * dcov[4];
+      dSig.c[2][0] = 0.5f * dcov[2];
+      dSig.c[2][1] = 0.5f * dcov[4];
+      dSig.c[2][2] = dcov[5];
+      Mat3 M2;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) M2.c[i][j] = 2.0f * Mm.c[i][j];
+      const Mat3 dL_dM = mat3_mul(M2, dSig);
+      const Mat3 Rt = mat3_T(R);
+      Mat3 dMt = mat3_T(dL_dM);
+      dscale.x = Rt.c[0][0] * dMt.c[0][0] + Rt.c[0][1] * dMt.c[0][1] + Rt.c[0][2] * dMt.c[0][2];
+      dscale.y = Rt.c[1][0] * dMt.c[1][0] + Rt.c[1][1] * dMt.c[1][1] + Rt.c[1][2] * dMt.c[1][2];
+      dscale.z = Rt.c[2][0] * dMt.c[2][0] + Rt.c[2][1] * dMt.c[2][1] + Rt.c[2][2] * dMt.c[2][2];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        dMt.c[0][j] *= s.x;
+        dMt.c[1][j] *= s.y;
+        dMt.c[2][j] *= s.z;
+      }
+      drot.x = 2 * z * (dMt.c[0][1] - dMt.c[1][0]) + 2 * y * (dMt.c[2][0] - dMt.c[0][2]) +
+               2 * x * (dMt.c[1][2] - dMt.c[2][1]);
+      drot.y = 2 * y * (dMt.c[1][0] + dMt.c[0][1]) + 2 * z * (dMt.c[2][0] + dMt.c[0][2]) +
+               2 * r * (dMt.c[1][2] - dMt.c[2][1]) - 4 * x * (dMt.c[2][2] + dMt.c[1][1]);
+      drot.z = 2 * x * (dMt.c[1][0] + dMt.c[0][1]) + 2 * r * (dMt.c[2][0] - dMt.c[0][2]) +
+               2 * z * (dMt.c[1][2] + dMt.c[2][1]) - 4 * y * (dMt.c[2][2] + dMt.c[0][0]);
+      drot.w = 2 * r * (dMt.c[0][1] - dMt.c[1][0]) + 2 * x * (dMt.c[2][0] + dMt.c[0][2]) +
+               2 * y * (dMt.c[1][2] + dMt.c[2][1]) - 4 * z * (dMt.c[1][1] + dMt.c[0][0]);
+    }
+  }
+  dL_dmean3D[3 * idx + 0] = dmean.x;
+  dL_dmean3D[3 * idx + 1] = dmean.y;
+  dL_dmean3D[3 * idx + 2] = dmean.z;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = dcov[k];
+  dL_dscale[3 * idx + 0] = dscale.x;
+  dL_dscale[3 * idx + 1] = dscale.y;
+  dL_dscale[3 * idx + 2] = dscale.z;
+  dL_drot[4 * idx + 0] = drot.x;
+  dL_drot[4 * idx + 1] = drot.y;
+  dL_drot[4 * idx + 2] = drot.z;
+  dL_drot[4 * idx + 3] = drot.w;
+}
+
+cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s) {
+  if (a.P == 0) return cudaSuccess;
+  const unsigned gx = (a.W + TILE_X - 1) / TILE_X, gy = (a.H + TILE_Y - 1) / TILE_Y;
+  const int T = gx * gy;
+  GeomWS g = GeomWS::from((char*)a.geom_ws, a.P);
+  ImgWS im = ImgWS::from((char*)a.img_ws, (size_t)a.W * a.H, T);
+  BinWS b = BinWS::from((char*)a.binning_ws, (size_t)a.R_cap);
+  const float focal_y = a.H / (2.0f * a.tan_fovy);
+  const float focal_x = a.W / (2.0f * a.tan_fovx);
+  const int* radii = a.radii ? a.radii : g.radii;
+  g_prof.begin(5, s);
+  render_bwd_kernel<<<T, 256, 0, s>>>(im.ranges, b.inst_geo, b.inst_attr, a.W, a.H, a.background, im.final_T,
+                                      im.n_contrib, a.dL_dpix, g.grad_acc);
+  g_prof.end(5, s);
+  g_prof.begin(6, s);
+  preprocess_bwd_kernel<<<(a.P + 127) / 128, 128, 0, s>>>(
+      a.P, a.D, a.M, a.means3D, radii, a.shs, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix,
+      a.projmatrix, focal_x, focal_y, a.tan_fovx, a.tan_fovy, a.cam_pos, g, a.dL_dmean2D, a.dL_dconic, a.dL_dopacity,
+      a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D, a.dL_dsh, a.dL_dscale, a.dL_drot);
+  g_prof.end(6, s);
+  return cudaGetLastError();
+}
+
+}  // namespace dgm

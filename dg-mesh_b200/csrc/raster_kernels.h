@@ -1,0 +1,67 @@
+// raster_kernels.h -- host-side launch interface between api.cu and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace dgm {
+
+struct FwdArgs {
+  int P, D, M;
+  const float* background;
+  int W, H;
+  const float *means3D, *shs, *colors_precomp, *opacities, *scales;
+  float scale_modifier;
+  const float *rotations, *cov3D_precomp, *viewmatrix, *projmatrix, *cam_pos;
+  float tan_fovx, tan_fovy;
+  int prefiltered;
+  float* out_color;
+  int* radii;
+  void *geom_ws, *binning_ws, *img_ws;
+  int64_t R_cap;
+  int32_t* status;
+};
+
+struct BwdArgs {
+  int P, D, M;
+  const float* background;
+  int W, H;
+  const float *means3D, *shs, *colors_precomp, *scales;
+  float scale_modifier;
+  const float *rotations, *cov3D_precomp, *viewmatrix, *projmatrix, *cam_pos;
+  float tan_fovx, tan_fovy;
+  const int* radii;
+  void *geom_ws, *binning_ws, *img_ws;
+  int64_t R_cap;
+  const float* dL_dpix;
+  float *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor, *dL_dmean3D, *dL_dcov3D, *dL_dsh, *dL_dscale, *dL_drot;
+};
+
+// event pairs around kernels (see dgm_profile_enable in include/dgmesh_b200.h)
+struct Profiler {
+  bool on = false;
+  cudaEvent_t ev[16][2] = {};
+  bool used[16] = {};
+  void begin(int k, cudaStream_t s) {
+    if (on) cudaEventRecord(ev[k][0], s);
+  }
+  void end(int k, cudaStream_t s) {
+    if (on) {
+      cudaEventRecord(ev[k][1], s);
+      used[k] = true;
+    }
+  }
+};
+extern Profiler g_prof;
+
+cudaError_t launch_forward(const FwdArgs& a, cudaStream_t s);
+cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s);
+cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, uint8_t* present,
+                                cudaStream_t s);
+cudaError_t launch_export_state(int P, int W, int H, int64_t R_cap, const void* geom_ws, const void* binning_ws,
+                                const void* img_ws, float* depths, float* means2D, float* cov3D, float* conic_opacity,
+                                float* rgb, uint32_t* tiles_touched, uint8_t* clamped, uint64_t* point_list_keys,
+                                uint32_t* point_list, uint32_t* ranges, float* final_T, uint32_t* n_contrib,
+                                cudaStream_t s);
+
+}  // namespace dgm

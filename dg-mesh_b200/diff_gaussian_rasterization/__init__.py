@@ -1,0 +1,348 @@
+"""Drop-in `diff_gaussian_rasterization` backed by libdgmesh_b200.so (sm_100a).
+
+Mirrors the reference Python surface
+(dgmesh/submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py):
+  GaussianRasterizationSettings  :157-169   same 12 fields, same order
+  GaussianRasterizer             :171-220   forward(...) -> (color, radii), markVisible
+  rasterize_gaussians / _RasterizeGaussians :21-155
+  _C.rasterize_gaussians / _C.rasterize_gaussians_backward / _C.mark_visible
+                                 (dgr/ext.cpp:15-19, dgr/rasterize_points.h:18-66)
+
+Differences that are deliberate:
+  * the autograd path never copies num_rendered to the host; R stays in a device
+    status block.  The instance workspace is sized from a high-water mark; an overflow
+    is detected when the status block is next read and raises (no silent truncation).
+    Set DGMESH_B200_SYNC=1 to size exactly with one host sync per forward, like the
+    reference (rasterizer_impl.cu:281).
+  * work is enqueued on the CURRENT torch stream (the reference uses the legacy
+    default stream).
+"""
+import os
+import sys
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+import _dgm_lib  # noqa: E402
+
+_ST_WORDS = 8
+
+
+def _f32c(t, name):
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    return t.contiguous()
+
+
+class _Sizing:
+    """High-water-mark capacity of the (Gaussian, tile) instance workspace per problem shape."""
+    hint = {}       # (device, P, W, H) -> R capacity
+    pending = []    # [(event, pinned status, key, R_cap)] forwards whose status was not read yet
+
+    @classmethod
+    def poll(cls, block=False):
+        still = []
+        for ev, host, key, cap in cls.pending:
+            if block:
+                ev.synchronize()
+            if ev.query():
+                R, ovf = int(host[0]), int(host[1])
+                cls.hint[key] = max(cls.hint.get(key, 0), _grow(R))
+                if ovf:
+                    cls.pending = []
+                    raise _dgm_lib.DgmError(
+                        f"rasterizer instance workspace overflowed in an earlier forward (R={R} > capacity {cap}); "
+                        "that render was background-only. Capacity has been raised; re-run the step "
+                        "(or set DGMESH_B200_SYNC=1 for exact sizing with a host sync).")
+            else:
+                still.append((ev, host, key, cap))
+        cls.pending = still
+
+
+def _round_cap(c):
+    # multiples of 32 instances keep every workspace array 128-byte sized, so the capacity can be
+    # recovered from the byte size of the binning buffer: bytes = 60 * R_cap + 128
+    return (int(c) + 31) // 32 * 32
+
+
+def _grow(R):
+    return _round_cap(int(R * 1.5) + (1 << 16))
+
+
+def _cap_from_bytes(nbytes):
+    return (int(nbytes) - 128) // 60
+
+
+def _raw_forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                 projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered, R_cap):
+    """One enqueue of dgr_forward.  Returns (color, radii, geom, binning, img, status)."""
+    lib = _dgm_lib.lib()
+    if means3D.ndim != 2 or means3D.shape[1] != 3:
+        raise ValueError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
+    dev = means3D.device
+    P = means3D.shape[0]
+    M = int(sh.shape[1]) if (sh is not None and sh.numel() != 0) else 0
+    gb, bb, ib = _dgm_lib.c_size_t(), _dgm_lib.c_size_t(), _dgm_lib.c_size_t()
+    _dgm_lib.check(lib.dgr_workspace_sizes(P, W, H, R_cap, gb, bb, ib), "dgr_workspace_sizes")
+    color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    geom = torch.empty((gb.value,), dtype=torch.uint8, device=dev)
+    binning = torch.empty((bb.value,), dtype=torch.uint8, device=dev)
+    img = torch.empty((ib.value,), dtype=torch.uint8, device=dev)
+    status = torch.empty((_ST_WORDS,), dtype=torch.int32, device=dev)
+    p = _dgm_lib.ptr
+    rc = lib.dgr_forward(P, degree, M, p(bg), W, H, p(means3D), p(sh), p(colors), p(opacity), p(scales),
+                         float(scale_modifier), p(rotations), p(cov3D_precomp), p(viewmatrix), p(projmatrix),
+                         p(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), p(color), p(radii),
+                         p(geom), gb.value, p(binning), bb.value, R_cap, p(img), ib.value, p(status),
+                         _dgm_lib.stream_ptr())
+    _dgm_lib.check(rc, "dgr_forward")
+    return color, radii, geom, binning, img, status
+
+
+def _forward_sized(args_fn, key, sync):
+    """Run the forward with a capacity policy.  args_fn(R_cap) enqueues and returns the tuple."""
+    _Sizing.poll()
+    cap = _Sizing.hint.get(key)
+    if cap is None or sync:
+        # first call for this shape (or strict mode): size exactly, one host sync
+        cap0 = cap if cap is not None else _round_cap(max(4 * key[1], 1 << 18))
+        out = args_fn(cap0)
+        st = out[-1].cpu()
+        R = int(st[0])
+        _Sizing.hint[key] = max(_Sizing.hint.get(key, 0), _grow(R))
+        if int(st[1]):
+            cap0 = _Sizing.hint[key]
+            out = args_fn(cap0)
+        return out, cap0, R
+    out = args_fn(cap)
+    host = torch.empty((_ST_WORDS,), dtype=torch.int32, pin_memory=True)
+    host.copy_(out[-1], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _Sizing.pending.append((ev, host, key, cap))
+    return out, cap, None
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        rs = raster_settings
+        means3D = _f32c(means3D, "means3D")
+        if means3D is None:
+            raise ValueError("means3D must have dimensions (num_points, 3)")
+        t = dict(bg=_f32c(rs.bg, "bg"), sh=_f32c(sh, "sh"), colors=_f32c(colors_precomp, "colors_precomp"),
+                 opac=_f32c(opacities, "opacities"), scales=_f32c(scales, "scales"),
+                 rots=_f32c(rotations, "rotations"), cov=_f32c(cov3Ds_precomp, "cov3D_precomp"),
+                 view=_f32c(rs.viewmatrix, "viewmatrix"), proj=_f32c(rs.projmatrix, "projmatrix"),
+                 campos=_f32c(rs.campos, "campos"))
+        H, W = int(rs.image_height), int(rs.image_width)
+        key = (means3D.device.index, means3D.shape[0], W, H)
+
+        def run(R_cap):
+            return _raw_forward(t["bg"], means3D, t["colors"], t["opac"], t["scales"], t["rots"], rs.scale_modifier,
+                                t["cov"], t["view"], t["proj"], rs.tanfovx, rs.tanfovy, H, W, t["sh"], rs.sh_degree,
+                                t["campos"], rs.prefiltered, R_cap)
+
+        sync = bool(rs.debug) or os.environ.get("DGMESH_B200_SYNC", "0") == "1"
+        (color, radii, geom, binning, img, status), cap, _ = _forward_sized(run, key, sync)
+        ctx.raster_settings = rs
+        ctx.R_cap = cap
+        ctx.tensors = t
+        ctx.save_for_backward(means3D, radii, geom, binning, img, status)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _):
+        rs = ctx.raster_settings
+        t = ctx.tensors
+        means3D, radii, geom, binning, img, status = ctx.saved_tensors
+        _Sizing.poll(block=True)  # the forward must not have overflowed (raises otherwise)
+        lib = _dgm_lib.lib()
+        P = means3D.shape[0]
+        H, W = int(rs.image_height), int(rs.image_width)
+        sh = t["sh"]
+        M = int(sh.shape[1]) if sh is not None else 0
+        dev = means3D.device
+        f = dict(dtype=torch.float32, device=dev)
+        g_m2d = torch.empty((P, 3), **f)
+        g_conic = torch.empty((P, 2, 2), **f)
+        g_opac = torch.empty((P, 1), **f)
+        g_col = torch.empty((P, 3), **f)
+        g_m3d = torch.empty((P, 3), **f)
+        g_cov = torch.empty((P, 6), **f)
+        g_sh = torch.empty((P, M, 3), **f)
+        g_scale = torch.empty((P, 3), **f)
+        g_rot = torch.empty((P, 4), **f)
+        dpix = _f32c(grad_out_color, "grad_out_color")
+        p = _dgm_lib.ptr
+        rc = lib.dgr_backward(P, rs.sh_degree, M, p(t["bg"]), W, H, p(means3D), p(sh), p(t["colors"]),
+                              p(t["scales"]), float(rs.scale_modifier), p(t["rots"]), p(t["cov"]), p(t["view"]),
+                              p(t["proj"]), p(t["campos"]), float(rs.tanfovx), float(rs.tanfovy), p(radii),
+                              p(geom), p(binning), ctx.R_cap, p(img), p(dpix), p(g_m2d), p(g_conic), p(g_opac),
+                              p(g_col), p(g_m3d), p(g_cov), p(g_sh), p(g_scale), p(g_rot), _dgm_lib.stream_ptr())
+        _dgm_lib.check(rc, "dgr_backward")
+        # same ordering as the reference (:143-153)
+        return (g_m3d, g_m2d, g_sh if sh is not None else None, g_col if t["colors"] is not None else None, g_opac,
+                g_scale if t["scales"] is not None else None, g_rot if t["rots"] is not None else None,
+                g_cov if t["cov"] is not None else None, None)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        # frustum test (reference :176-185)
+        with torch.no_grad():
+            rs = self.raster_settings
+            return _C.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        raster_settings = self.raster_settings
+        # same argument-exclusivity errors as the reference (:191-195)
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   raster_settings)
+
+
+class _CCompat:
+    """`diff_gaussian_rasterization._C` with the reference's three entry points and tuple
+    layouts (dgr/rasterize_points.h:18-66).  These return num_rendered as a Python int and
+    therefore synchronise, exactly like the reference binding."""
+
+    @staticmethod
+    def rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                            viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree,
+                            campos, prefiltered, debug):
+        a = [_f32c(x, n) for x, n in ((bg, "bg"), (means3D, "means3D"), (colors, "colors"), (opacity, "opacity"),
+                                      (scales, "scales"), (rotations, "rotations"), (cov3D_precomp, "cov3D"),
+                                      (viewmatrix, "view"), (projmatrix, "proj"), (sh, "sh"), (campos, "campos"))]
+        bg_, m3, col, op, sc, ro, cov, view, proj, sh_, cam = a
+        if m3 is None:
+            raise ValueError("means3D must have dimensions (num_points, 3)")
+        key = (m3.device.index, m3.shape[0], int(image_width), int(image_height))
+
+        def run(R_cap):
+            return _raw_forward(bg_, m3, col, op, sc, ro, scale_modifier, cov, view, proj, tan_fovx, tan_fovy,
+                                int(image_height), int(image_width), sh_, degree, cam, prefiltered, R_cap)
+
+        (color, radii, geom, binning, img, status), cap, R = _forward_sized(run, key, True)
+        # the three opaque byte tensors carry everything backward needs (capacity is implied by
+        # the size of the binning buffer)
+        return R, color, radii, geom, binning, img
+
+    @staticmethod
+    def rasterize_gaussians_backward(bg, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                                     viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
+                                     geomBuffer, R, binningBuffer, imageBuffer, debug):
+        lib = _dgm_lib.lib()
+        binning = binningBuffer
+        cap = _cap_from_bytes(binning.numel())
+        m3 = _f32c(means3D, "means3D")
+        P = m3.shape[0]
+        H, W = int(dL_dout_color.shape[1]), int(dL_dout_color.shape[2])
+        sh_ = _f32c(sh, "sh")
+        M = int(sh_.shape[1]) if sh_ is not None else 0
+        f = dict(dtype=torch.float32, device=m3.device)
+        g_m2d, g_conic, g_opac = torch.empty((P, 3), **f), torch.empty((P, 2, 2), **f), torch.empty((P, 1), **f)
+        g_col, g_m3d, g_cov = torch.empty((P, 3), **f), torch.empty((P, 3), **f), torch.empty((P, 6), **f)
+        g_sh, g_scale, g_rot = torch.empty((P, M, 3), **f), torch.empty((P, 3), **f), torch.empty((P, 4), **f)
+        p = _dgm_lib.ptr
+        rc = lib.dgr_backward(P, degree, M, p(_f32c(bg, "bg")), W, H, p(m3), p(sh_), p(_f32c(colors, "colors")),
+                              p(_f32c(scales, "scales")), float(scale_modifier), p(_f32c(rotations, "rotations")),
+                              p(_f32c(cov3D_precomp, "cov3D")), p(_f32c(viewmatrix, "view")),
+                              p(_f32c(projmatrix, "proj")), p(_f32c(campos, "campos")), float(tan_fovx),
+                              float(tan_fovy), p(radii.contiguous()), p(geomBuffer), p(binning), cap, p(imageBuffer),
+                              p(_f32c(dL_dout_color, "dL_dout_color")), p(g_m2d), p(g_conic), p(g_opac), p(g_col),
+                              p(g_m3d), p(g_cov), p(g_sh), p(g_scale), p(g_rot), _dgm_lib.stream_ptr())
+        _dgm_lib.check(rc, "dgr_backward")
+        return g_m2d, g_col, g_opac, g_m3d, g_cov, g_sh, g_scale, g_rot
+
+    @staticmethod
+    def mark_visible(means3D, viewmatrix, projmatrix):
+        lib = _dgm_lib.lib()
+        m3 = _f32c(means3D, "means3D")
+        P = 0 if m3 is None else m3.shape[0]
+        present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+        if P:
+            rc = lib.dgr_mark_visible(P, m3.data_ptr(), _f32c(viewmatrix, "view").data_ptr(),
+                                      _f32c(projmatrix, "proj").data_ptr(), present.data_ptr(),
+                                      _dgm_lib.stream_ptr())
+            _dgm_lib.check(rc, "dgr_mark_visible")
+        return present
+
+
+_C = _CCompat()
+
+
+def export_state(P, W, H, R_cap, geom, binning, img, R):
+    """Parity-test helper: reference-visible intermediate state of a forward as a dict of tensors."""
+    lib = _dgm_lib.lib()
+    dev = geom.device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    o = dict(
+        depths=torch.zeros(P, device=dev), means2D=torch.zeros(P, 2, device=dev),
+        cov3D=torch.zeros(P, 6, device=dev), conic_opacity=torch.zeros(P, 4, device=dev),
+        rgb=torch.zeros(P, 3, device=dev), tiles_touched=torch.zeros(P, dtype=torch.int32, device=dev),
+        clamped=torch.zeros(P, 3, dtype=torch.uint8, device=dev),
+        point_list_keys=torch.zeros(max(R_cap, 1), dtype=torch.int64, device=dev),
+        point_list=torch.zeros(max(R_cap, 1), dtype=torch.int32, device=dev),
+        ranges=torch.zeros(T, 2, dtype=torch.int32, device=dev), final_T=torch.zeros(H * W, device=dev),
+        n_contrib=torch.zeros(H * W, dtype=torch.int32, device=dev))
+    p = _dgm_lib.ptr
+    rc = lib.dgr_export_state(P, W, H, R_cap, p(geom), p(binning), p(img), p(o["depths"]), p(o["means2D"]),
+                              p(o["cov3D"]), p(o["conic_opacity"]), p(o["rgb"]), p(o["tiles_touched"]),
+                              p(o["clamped"]), p(o["point_list_keys"]), p(o["point_list"]), p(o["ranges"]),
+                              p(o["final_T"]), p(o["n_contrib"]), _dgm_lib.stream_ptr())
+    _dgm_lib.check(rc, "dgr_export_state")
+    o["point_list_keys"] = o["point_list_keys"][:R]
+    o["point_list"] = o["point_list"][:R]
+    return o

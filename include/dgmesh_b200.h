@@ -1,0 +1,152 @@
+/*
+ * dgmesh_b200.h -- C-ABI of the B200-native DG-Mesh hot path (libdgmesh_b200.so).
+ *
+ * Drop-in boundary: every entry point below stands in for one native interface
+ * of the reference (Isabella98Liu/DG-Mesh @ 754f42c); the reference file:line it
+ * replaces is cited on each declaration.  Conventions (all entry points):
+ *
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the name ends in `_host`; no torch / C++ types cross this boundary;
+ *   - the library never allocates, never frees and never synchronises: the
+ *     caller owns all memory (query-then-call workspaces) and passes the CUDA
+ *     stream (`void* stream` == cudaStream_t) the work is enqueued on;
+ *   - "absent" optional inputs are NULL (the reference passes zero-element
+ *     tensors whose data_ptr is null, dgr/rasterize_points.cu:84-103);
+ *   - return value: 0 on success, a negative DGM_E_* code on a host-detectable
+ *     error (bad argument, launch failure).  Device-side conditions (workspace
+ *     overflow) are reported through the `status` words, see dgr_forward.
+ *
+ * Layouts are the reference's: row-major contiguous fp32 / int32 tensors.
+ */
+#ifndef DGMESH_B200_H_
+#define DGMESH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGM_OK 0
+#define DGM_E_BADARG (-1)
+#define DGM_E_WORKSPACE (-2) /* a workspace is smaller than the query says */
+#define DGM_E_LAUNCH (-3)    /* cudaGetLastError() != cudaSuccess after enqueue */
+
+/* library / build identification ("dgmesh_b200 <ver> sm_100a") */
+const char* dgm_version(void);
+/* cudaGetErrorString of the last launch error seen by this thread (or "") */
+const char* dgm_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Differentiable 3D-Gaussian rasterizer
+ * replaces CudaRasterizer::Rasterizer (dgr/cuda_rasterizer/rasterizer.h:20-86,
+ * implementation dgr/cuda_rasterizer/rasterizer_impl.cu:198-336, 340-434) and
+ * the torch binding dgr/rasterize_points.cu:35-217.
+ * ------------------------------------------------------------------------ */
+
+/* device status block written by dgr_forward (int32[DGR_STATUS_WORDS]) */
+#define DGR_STATUS_WORDS 8
+#define DGR_ST_NUM_RENDERED 0 /* R = sum of tiles touched (reference: num_rendered,
+                                 rasterizer_impl.cu:281) -- stays on the device */
+#define DGR_ST_OVERFLOW 1     /* 1 if R > R_cap: binning + blend were skipped */
+#define DGR_ST_MAX_TILE 2     /* longest per-tile list (diagnostic) */
+
+/* Workspace sizes for P Gaussians, W x H image and room for R_cap
+ * (Gaussian, tile) instances.  Mirrors required<GeometryState/ImageState/
+ * BinningState>() (rasterizer_impl.h:66-72).  The three buffers play the role
+ * of the reference's geomBuffer / binningBuffer / imgBuffer byte tensors
+ * (rasterize_points.cu:68-78); their internal layout is private to this
+ * library and they must be handed unchanged to dgr_backward. */
+int dgr_workspace_sizes(int P, int W, int H, int64_t R_cap,
+                        size_t* geom_bytes, size_t* binning_bytes, size_t* img_bytes);
+
+/* Forward: preprocess -> per-tile binning/sort -> alpha-composite.
+ * Same inputs / outputs as Rasterizer::forward (rasterizer.h:28-52):
+ *   P, D (active SH degree), M (SH coeffs per Gaussian, 0 if shs == NULL)
+ *   background[3], means3D[P,3], shs[P,M,3] | colors_precomp[P,3],
+ *   opacities[P], scales[P,3] + rotations[P,4] | cov3D_precomp[P,6],
+ *   viewmatrix[16], projmatrix[16] (row-vector convention, read column-major,
+ *   auxiliary.h:58-77), cam_pos[3]
+ *   -> out_color[3,H,W], radii[P] (int32; may be NULL)
+ * No host synchronisation: where the reference copies num_rendered to the host
+ * (rasterizer_impl.cu:281) this writes it to status[DGR_ST_NUM_RENDERED].  If
+ * R exceeds R_cap, status[DGR_ST_OVERFLOW] = 1, out_color is filled with the
+ * background and the caller must retry with a larger R_cap. */
+int dgr_forward(int P, int D, int M,
+                const float* background, int W, int H,
+                const float* means3D, const float* shs, const float* colors_precomp,
+                const float* opacities, const float* scales, float scale_modifier,
+                const float* rotations, const float* cov3D_precomp,
+                const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                float tan_fovx, float tan_fovy, int prefiltered,
+                float* out_color, int* radii,
+                void* geom_ws, size_t geom_bytes,
+                void* binning_ws, size_t binning_bytes, int64_t R_cap,
+                void* img_ws, size_t img_bytes,
+                int32_t* status, void* stream);
+
+/* Backward: same contract as Rasterizer::backward (rasterizer.h:54-84).  All
+ * nine gradient outputs are fully written (zeros for culled Gaussians), the
+ * caller does NOT need to zero them (the reference requires zero-filled
+ * tensors, rasterize_points.cu:151-159).
+ *   dL_dpix[3,H,W] -> dL_dmean2D[P,3] (.xy written, .z = 0), dL_dconic[P,4],
+ *   dL_dopacity[P], dL_dcolor[P,3], dL_dmean3D[P,3], dL_dcov3D[P,6],
+ *   dL_dsh[P,M,3] (may be NULL when shs == NULL), dL_dscale[P,3], dL_drot[P,4] */
+int dgr_backward(int P, int D, int M,
+                 const float* background, int W, int H,
+                 const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* scales, float scale_modifier, const float* rotations,
+                 const float* cov3D_precomp,
+                 const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                 float tan_fovx, float tan_fovy, const int* radii,
+                 void* geom_ws, void* binning_ws, int64_t R_cap, void* img_ws,
+                 const float* dL_dpix,
+                 float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                 float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                 float* dL_dscale, float* dL_drot,
+                 void* stream);
+
+/* Frustum test, Rasterizer::markVisible (rasterizer.h:22-27,
+ * rasterizer_impl.cu:54-66,141-153): present[P] (uint8 bool). */
+int dgr_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* Introspection for parity tests: export the reference-visible intermediate
+ * state of the last forward from the private workspaces into caller arrays
+ * laid out as in the reference's GeometryState / BinningState / ImageState
+ * (rasterizer_impl.h:30-63).  Any output pointer may be NULL.
+ *   depths[P], means2D[P,2], cov3D[P,6], conic_opacity[P,4], rgb[P,3],
+ *   tiles_touched[P] (u32), clamped[P,3] (u8),
+ *   point_list_keys[R] (u64: tile<<32 | depth bits), point_list[R] (u32),
+ *   ranges[T,2] (u32), final_T[H*W], n_contrib[H*W] (u32)               */
+int dgr_export_state(int P, int W, int H, int64_t R_cap,
+                     const void* geom_ws, const void* binning_ws, const void* img_ws,
+                     float* depths, float* means2D, float* cov3D, float* conic_opacity,
+                     float* rgb, uint32_t* tiles_touched, uint8_t* clamped,
+                     uint64_t* point_list_keys, uint32_t* point_list,
+                     uint32_t* ranges, float* final_T, uint32_t* n_contrib,
+                     void* stream);
+
+/* ------------------------------------------------------------------------
+ * Measurement hooks (bench.py roofline leg).  Off by default.  When enabled the
+ * library records a CUDA event pair around each of its kernels ON THE LAUNCHING
+ * STREAM; dgm_profile_read synchronises those events (the only call in this
+ * library that waits on the device) and returns the duration in ms of the most
+ * recent launch of kernel k, k in DGM_K_*; -1 if it never ran.
+ * ------------------------------------------------------------------------ */
+#define DGM_K_PREPROCESS 0
+#define DGM_K_TILE_SCAN 1
+#define DGM_K_SCATTER 2
+#define DGM_K_SORT_PACK 3
+#define DGM_K_RENDER_FWD 4
+#define DGM_K_RENDER_BWD 5
+#define DGM_K_PREPROCESS_BWD 6
+#define DGM_K_COUNT 16
+int dgm_profile_enable(int on);
+int dgm_profile_read(float* ms_host, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGMESH_B200_H_ */

@@ -1,0 +1,113 @@
+"""numpy front-end of the CPU oracle (oracle/liboracle.so, built from raster_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/README.md.  Nothing under dg-mesh_b200/ may
+import this module.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `make oracle/liboracle.so`")
+        _LIB = ctypes.CDLL(path)
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class RasterOracle:
+    """precision: 32 (reference op order in fp32) or 64 (same algorithm in fp64)."""
+
+    def __init__(self, precision=32):
+        assert precision in (32, 64)
+        self.prec = precision
+        self.dt = np.float32 if precision == 32 else np.float64
+        self.creal = ctypes.c_float if precision == 32 else ctypes.c_double
+
+    def _fn(self, name):
+        return getattr(_lib(), f"{name}_{self.prec}")
+
+    def forward(self, means3D, opacities, view, proj, campos, W, H, tan_fovx, tan_fovy, bg, shs=None, degree=0,
+                colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0):
+        dt, cr = self.dt, self.creal
+        means3D = _c(means3D, dt)
+        P = means3D.shape[0]
+        shs_, col_ = _c(shs, dt), _c(colors_precomp, dt)
+        M = 0 if shs_ is None else shs_.shape[1]
+        sc_, ro_, cv_ = _c(scales, dt), _c(rotations, dt), _c(cov3D_precomp, dt)
+        op_ = _c(np.asarray(opacities).reshape(-1), dt)
+        view_, proj_, cam_, bg_ = _c(view, dt).reshape(-1), _c(proj, dt).reshape(-1), _c(campos, dt), _c(bg, dt)
+        o = dict(radii=np.zeros(P, np.int32), means2D=np.zeros((P, 2), dt), depths=np.zeros(P, dt),
+                 cov3D=np.zeros((P, 6), dt), rgb=np.zeros((P, 3), dt), conic_opacity=np.zeros((P, 4), dt),
+                 tiles_touched=np.zeros(P, np.uint32), clamped=np.zeros((P, 3), np.uint8))
+        f = self._fn("orc_preprocess")
+        f.restype = None
+        f(ctypes.c_int(P), ctypes.c_int(degree), ctypes.c_int(M), _p(means3D), _p(sc_), cr(scale_modifier), _p(ro_),
+          _p(op_), _p(shs_), _p(cv_), _p(col_), _p(view_), _p(proj_), _p(cam_), ctypes.c_int(W), ctypes.c_int(H),
+          cr(tan_fovx), cr(tan_fovy), _p(o["radii"]), _p(o["means2D"]), _p(o["depths"]), _p(o["cov3D"]), _p(o["rgb"]),
+          _p(o["conic_opacity"]), _p(o["tiles_touched"]), _p(o["clamped"]))
+        R = int(o["tiles_touched"].astype(np.int64).sum())
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        o["point_list_keys"] = np.zeros(max(R, 1), np.uint64)
+        o["point_list"] = np.zeros(max(R, 1), np.uint32)
+        o["ranges"] = np.zeros((T, 2), np.uint32)
+        fb = self._fn("orc_bin")
+        fb.restype = ctypes.c_int64
+        n = fb(ctypes.c_int(P), ctypes.c_int(W), ctypes.c_int(H), _p(o["radii"]), _p(o["means2D"]), _p(o["depths"]),
+               _p(o["point_list_keys"]), _p(o["point_list"]), _p(o["ranges"]), ctypes.c_int64(max(R, 1)))
+        assert n == R, (n, R)
+        o["point_list_keys"], o["point_list"] = o["point_list_keys"][:R], o["point_list"][:R]
+        o["num_rendered"] = R
+        feats = col_ if col_ is not None else o["rgb"]
+        o["final_T"] = np.zeros(H * W, dt)
+        o["n_contrib"] = np.zeros(H * W, np.uint32)
+        o["color"] = np.zeros((3, H, W), dt)
+        fr = self._fn("orc_render_fwd")
+        fr.restype = None
+        fr(ctypes.c_int(W), ctypes.c_int(H), _p(o["ranges"]), _p(o["point_list"]), _p(o["means2D"]), _p(feats),
+           _p(o["conic_opacity"]), _p(bg_), _p(o["final_T"]), _p(o["n_contrib"]), _p(o["color"]))
+        o["_inputs"] = dict(means3D=means3D, shs=shs_, colors=col_, scales=sc_, rotations=ro_, cov3D_precomp=cv_,
+                            view=view_, proj=proj_, campos=cam_, bg=bg_, W=W, H=H, tan_fovx=tan_fovx,
+                            tan_fovy=tan_fovy, degree=degree, M=M, scale_modifier=scale_modifier, feats=feats)
+        return o
+
+    def backward(self, fwd, dL_dpix):
+        dt, cr = self.dt, self.creal
+        i = fwd["_inputs"]
+        P, W, H, M = i["means3D"].shape[0], i["W"], i["H"], i["M"]
+        dpix = _c(dL_dpix, dt)
+        g = dict(dL_dmean2D=np.zeros((P, 3), dt), dL_dconic=np.zeros((P, 4), dt), dL_dopacity=np.zeros(P, dt),
+                 dL_dcolor=np.zeros((P, 3), dt), dL_dmean3D=np.zeros((P, 3), dt), dL_dcov3D=np.zeros((P, 6), dt),
+                 dL_dsh=np.zeros((P, max(M, 1), 3), dt), dL_dscale=np.zeros((P, 3), dt), dL_drot=np.zeros((P, 4), dt))
+        f = self._fn("orc_render_bwd")
+        f.restype = None
+        f(ctypes.c_int(P), ctypes.c_int(W), ctypes.c_int(H), _p(fwd["ranges"]), _p(fwd["point_list"]), _p(i["bg"]),
+          _p(fwd["means2D"]), _p(fwd["conic_opacity"]), _p(i["feats"]), _p(fwd["final_T"]), _p(fwd["n_contrib"]),
+          _p(dpix), _p(g["dL_dmean2D"]), _p(g["dL_dconic"]), _p(g["dL_dopacity"]), _p(g["dL_dcolor"]))
+        cov3D = i["cov3D_precomp"] if i["cov3D_precomp"] is not None else fwd["cov3D"]
+        f2 = self._fn("orc_preprocess_bwd")
+        f2.restype = None
+        f2(ctypes.c_int(P), ctypes.c_int(i["degree"]), ctypes.c_int(M), _p(i["means3D"]), _p(fwd["radii"]),
+           _p(i["shs"]), _p(fwd["clamped"]), _p(i["scales"]), _p(i["rotations"]), cr(i["scale_modifier"]), _p(cov3D),
+           _p(i["view"]), _p(i["proj"]), ctypes.c_int(W), ctypes.c_int(H), cr(i["tan_fovx"]), cr(i["tan_fovy"]),
+           _p(i["campos"]), _p(g["dL_dmean2D"]), _p(g["dL_dconic"]), _p(g["dL_dcolor"]), _p(g["dL_dmean3D"]),
+           _p(g["dL_dcov3D"]), _p(g["dL_dsh"]) if i["shs"] is not None else None, _p(g["dL_dscale"]),
+           _p(g["dL_drot"]))
+        if M == 0:
+            g["dL_dsh"] = np.zeros((P, 0, 3), dt)
+        return g

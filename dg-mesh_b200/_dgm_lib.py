@@ -30,7 +30,8 @@ SIGNATURES = {
     "dgm_profile_read": (c_int, [ctypes.POINTER(c_float), c_int]),
 }
 
-KERNEL_NAMES = ["preprocess", "tile_scan", "scatter", "sort_pack", "render_fwd", "render_bwd", "preprocess_bwd"]
+KERNEL_NAMES = ["preprocess", "tile_scan", "scatter", "sort_pack", "render_fwd", "render_bwd", "preprocess_bwd",
+                "count"]
 
 
 def profile_read():

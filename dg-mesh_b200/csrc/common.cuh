@@ -52,25 +52,27 @@ struct GeomWS {
   }
 };
 
-// per-image state (ImageState, rasterizer_impl.h:47-54) + per-tile counters
+// per-image state (ImageState, rasterizer_impl.h:47-54) + binning tables
 struct ImgWS {
   float* final_T;        // [H*W]
   uint32_t* n_contrib;   // [H*W]
   uint2* ranges;         // [T]
-  uint32_t* tile_counts; // [T]   } zeroed together with one memset
-  uint32_t* tile_fill;   // [T]   }
-  uint32_t* ticket;      // [4]   }
-  size_t zero_bytes;     // bytes to clear starting at tile_counts
+  uint32_t* hist;        // [T, 256] (tile, depth bucket) counts -> block offsets -> block ends
+  uint32_t* depth_range; // [8]  {~min depth bits, max depth bits} of the visible set (follows hist: one memset)
+  uint32_t* tile_total;  // [T] instances per tile
+  uint32_t* tile_order;  // [T] tile ids, longest list first (launch order of the blend kernels)
+  uint32_t* scan_flags;  // [8]  completion ticket of tile_scan_kernel
   __host__ __device__ static ImgWS from(char* base, size_t npix, size_t T, size_t* bytes = nullptr) {
     char* p = base;
     ImgWS w;
     w.final_T = carve<float>(p, npix);
     w.n_contrib = carve<uint32_t>(p, npix);
     w.ranges = carve<uint2>(p, T);
-    w.tile_counts = carve<uint32_t>(p, 2 * T + 4);
-    w.tile_fill = w.tile_counts + T;
-    w.ticket = w.tile_counts + 2 * T;
-    w.zero_bytes = (2 * T + 4) * sizeof(uint32_t);
+    w.hist = carve<uint32_t>(p, T * 256 + 8);
+    w.depth_range = w.hist + T * 256;
+    w.tile_total = carve<uint32_t>(p, T);
+    w.tile_order = carve<uint32_t>(p, T);
+    w.scan_flags = carve<uint32_t>(p, 8);
     if (bytes) *bytes = size_t(p - base) + 128;
     return w;
   }

@@ -22,51 +22,71 @@ namespace dgm {
 #define RB 256
 #define ACC_STRIDE 9
 
-// Reduce 9 per-lane values over the warp.  On return lane (4*k) holds the total of
-// v[k] for k = 0..7 in `r8`, and every lane holds the total of v[8] in `r9`.
-__device__ __forceinline__ void warp_reduce9(const float (&v)[9], unsigned lane, float& r8, float& r9) {
+// Reduce the 9 partial gradients of TWO Gaussians (A, B) over the 32 lanes of a warp with a
+// transposing butterfly: at each level a lane keeps half of its values and trades the other
+// half with its partner, so 16 values cost 8+4+2+1+1 = 16 shuffles (+5 for the pair of 9th
+// values) instead of 2 x 9 x 5 = 90 for naive per-value reductions.
+// On return, for lanes with (lane & 1) == 0: r8 = total of value ((lane>>1)&7) of Gaussian
+// (lane>>4); r9 = total of value 8 of Gaussian (lane>>4) on every lane.
+__device__ __forceinline__ void warp_reduce_pair(const float (&vA)[9], const float (&vB)[9], unsigned lane, float& r8,
+                                                 float& r9) {
   const unsigned FULL = 0xffffffffu;
-  float a[4];
+  float a[8];
   {
     const bool up = lane & 16;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float send = up ? v[k] : v[k + 4];
-      const float keep = up ? v[k + 4] : v[k];
+    for (int k = 0; k < 8; ++k) {
+      const float send = up ? vA[k] : vB[k];
+      const float keep = up ? vB[k] : vA[k];
       a[k] = keep + __shfl_xor_sync(FULL, send, 16);
     }
   }
-  float b[2];
+  float b[4];
   {
     const bool up = lane & 8;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float send = up ? a[k] : a[k + 2];
-      const float keep = up ? a[k + 2] : a[k];
+    for (int k = 0; k < 4; ++k) {
+      const float send = up ? a[k] : a[k + 4];
+      const float keep = up ? a[k + 4] : a[k];
       b[k] = keep + __shfl_xor_sync(FULL, send, 8);
     }
   }
-  float c;
+  float c[2];
   {
     const bool up = lane & 4;
-    const float send = up ? b[0] : b[1];
-    const float keep = up ? b[1] : b[0];
-    c = keep + __shfl_xor_sync(FULL, send, 4);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float send = up ? b[k] : b[k + 2];
+      const float keep = up ? b[k + 2] : b[k];
+      c[k] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
   }
-  c += __shfl_xor_sync(FULL, c, 2);
-  c += __shfl_xor_sync(FULL, c, 1);
-  r8 = c;  // value index = (bit4 ? 4 : 0) + (bit3 ? 2 : 0) + (bit2 ? 1 : 0)
-  float d = v[8];
-  d += __shfl_xor_sync(FULL, d, 16);
-  d += __shfl_xor_sync(FULL, d, 8);
-  d += __shfl_xor_sync(FULL, d, 4);
-  d += __shfl_xor_sync(FULL, d, 2);
+  float d;
+  {
+    const bool up = lane & 2;
+    const float send = up ? c[0] : c[1];
+    const float keep = up ? c[1] : c[0];
+    d = keep + __shfl_xor_sync(FULL, send, 2);
+  }
   d += __shfl_xor_sync(FULL, d, 1);
-  r9 = d;
+  r8 = d;
+  float e;
+  {
+    const bool up = lane & 16;
+    const float send = up ? vA[8] : vB[8];
+    const float keep = up ? vB[8] : vA[8];
+    e = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+  e += __shfl_xor_sync(FULL, e, 8);
+  e += __shfl_xor_sync(FULL, e, 4);
+  e += __shfl_xor_sync(FULL, e, 2);
+  e += __shfl_xor_sync(FULL, e, 1);
+  r9 = e;
 }
 
-__global__ void __launch_bounds__(256) render_bwd_kernel(
-    const uint2* __restrict__ ranges, const float4* __restrict__ inst_geo, const float4* __restrict__ inst_attr,
+__global__ void __launch_bounds__(256, 3) render_bwd_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const float4* __restrict__ inst_geo,
+    const float4* __restrict__ inst_attr,
     int W, int H, const float* __restrict__ bg_color, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels, float4* __restrict__ grad_acc) {
   __shared__ __align__(128) float4 s_geo[2][RB];
@@ -76,7 +96,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
   __shared__ int s_maxc;
 
   const unsigned gx = (W + TILE_X - 1) / TILE_X;
-  const unsigned tile = blockIdx.x;
+  const unsigned tile = tile_order[blockIdx.x];  // longest lists first
   const unsigned tx = tile % gx, ty = tile / gx;
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wx0 = tx * TILE_X + (wid & 1) * 8, wy0 = ty * TILE_Y + (wid >> 1) * 4;
@@ -85,6 +105,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
   const uint32_t pix_id = W * py + px;
   const float pixfx = (float)px, pixfy = (float)py;
   const float bx0 = (float)wx0, bx1 = (float)(wx0 + 7), by0 = (float)wy0, by1 = (float)(wy0 + 3);
+  const float2 npx2 = make_float2(-pixfx, -pixfx), npy2 = make_float2(-pixfy, -pixfy);
 
   const uint2 range = ranges[tile];
   const int total = range.y - range.x;
@@ -167,46 +188,63 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
       }
       keep[k] = __ballot_sync(0xffffffffu, kp);
     }
-    // ---- back to front
+    // ---- back to front, two records per iteration (packed fp32x2 quadratic form, one
+    // butterfly reduction for both).  A is the record nearer the back (processed first).
 #pragma unroll
     for (int k = RB / 32 - 1; k >= 0; --k) {
       unsigned mask = keep[k];
       while (mask) {
-        const int bit = 31 - __clz(mask);
-        mask &= ~(1u << bit);
-        const int j = k * 32 + bit;
-        const int pos = lo + j;  // 0-based position in the tile list
-        const float4 ge = s_geo[st][j];
-        const float4 con_o = s_attr[st][2 * j];
-        const float4 col = s_attr[st][2 * j + 1];
-        float v[9];
+        const int bA = 31 - __clz(mask);
+        mask &= ~(1u << bA);
+        const bool two = mask != 0;
+        const int bB = two ? 31 - __clz(mask) : bA;
+        mask &= ~(1u << bB);
+        const int jA = k * 32 + bA, jB = k * 32 + bB;
+        const float4 geA = s_geo[st][jA], geB = s_geo[st][jB];
+        const float4 coA = s_attr[st][2 * jA], coB = s_attr[st][2 * jB];
+        const float2 dx2 = __fadd2_rn(make_float2(geA.x, geB.x), npx2);
+        const float2 dy2 = __fadd2_rn(make_float2(geA.y, geB.y), npy2);
+        float2 m1 = __fmul2_rn(dy2, make_float2(coA.z, coB.z));
+        const float2 m2 = __fmul2_rn(dx2, make_float2(coA.x, coB.x));
+        m1 = __fmul2_rn(dy2, m1);
+        const float2 sq = __ffma2_rn(dx2, m2, m1);
+        float2 m3 = __fmul2_rn(dx2, make_float2(coA.y, coB.y));
+        m3 = __fmul2_rn(dy2, m3);
+        const float2 npow = __ffma2_rn(sq, make_float2(0.5f, 0.5f), m3);  // = -power
+        float v[2][9];
 #pragma unroll
-        for (int q = 0; q < 9; ++q) v[q] = 0.f;
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int i = 0; i < 9; ++i) v[q][i] = 0.f;
         bool contrib = false;
-        // reference: contributor (1-based) must be <= last_contributor
-        if (pos < last_contributor) {
-          const float dx = ge.x - pixfx, dy = ge.y - pixfy;
-          const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
-          if (!(power > 0.0f)) {
-            const float G = expf(power);
-            const float alpha = min(0.99f, con_o.w * G);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float np = q ? npow.y : npow.x;
+          const float4 con_o = q ? coB : coA;
+          const float dx = q ? dx2.y : dx2.x, dy = q ? dy2.y : dy2.x;
+          const int j = q ? jB : jA;
+          // reference: contributor (0-based position) must be < last_contributor
+          if ((q == 0 || two) && (lo + j) < last_contributor && !(np < 0.0f)) {
+            const float G = expf(-np);
+            const float alpha = fminf(0.99f, con_o.w * G);
             if (!(alpha < 1.0f / 255.0f)) {
               contrib = true;
+              const float4 col = s_attr[st][2 * j + 1];
               T = T / (1.f - alpha);
               const float dchannel_dcolor = alpha * T;
               float dL_dalpha = 0.0f;
               accum0 = last_alpha * lc0 + (1.f - last_alpha) * accum0;
               lc0 = col.x;
               dL_dalpha += (col.x - accum0) * dLp0;
-              v[6] = dchannel_dcolor * dLp0;
+              v[q][6] = dchannel_dcolor * dLp0;
               accum1 = last_alpha * lc1 + (1.f - last_alpha) * accum1;
               lc1 = col.y;
               dL_dalpha += (col.y - accum1) * dLp1;
-              v[7] = dchannel_dcolor * dLp1;
+              v[q][7] = dchannel_dcolor * dLp1;
               accum2 = last_alpha * lc2 + (1.f - last_alpha) * accum2;
               lc2 = col.z;
               dL_dalpha += (col.z - accum2) * dLp2;
-              v[8] = dchannel_dcolor * dLp2;
+              v[q][8] = dchannel_dcolor * dLp2;
               dL_dalpha *= T;
               last_alpha = alpha;
               dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
@@ -215,21 +253,23 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
               const float gdy = G * dy;
               const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
               const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-              v[0] = dL_dG * dG_ddelx * ddelx_dx;
-              v[1] = dL_dG * dG_ddely * ddely_dy;
-              v[2] = -0.5f * gdx * dx * dL_dG;
-              v[3] = -0.5f * gdx * dy * dL_dG;
-              v[4] = -0.5f * gdy * dy * dL_dG;
-              v[5] = G * dL_dalpha;
+              v[q][0] = dL_dG * dG_ddelx * ddelx_dx;
+              v[q][1] = dL_dG * dG_ddely * ddely_dy;
+              v[q][2] = -0.5f * gdx * dx * dL_dG;
+              v[q][3] = -0.5f * gdx * dy * dL_dG;
+              v[q][4] = -0.5f * gdy * dy * dL_dG;
+              v[q][5] = G * dL_dalpha;
             }
           }
         }
         if (__any_sync(0xffffffffu, contrib)) {
           float r8, r9;
-          warp_reduce9(v, lane, r8, r9);
-          float* acc = &s_acc[j * ACC_STRIDE];
-          if ((lane & 3) == 0) atomicAdd(&acc[((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)], r8);
-          if (lane == 1) atomicAdd(&acc[8], r9);
+          warp_reduce_pair(v[0], v[1], lane, r8, r9);
+          const int jj = (lane & 16) ? jB : jA;
+          float* acc = &s_acc[jj * ACC_STRIDE];
+          // a lone record (two == false) reduces against zeros: only its own half is added
+          if ((lane & 1) == 0 && (two || !(lane & 16))) atomicAdd(&acc[(lane >> 1) & 7], r8);
+          if ((lane & 15) == 1 && (two || !(lane & 16))) atomicAdd(&acc[8], r9);
         }
       }
     }
@@ -258,9 +298,8 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
 
 // ===================================================== preprocess (bwd) ====
 // SH colour gradient (backward.cu:20-139): returns dL/d(mean) contribution, writes dL_dsh.
-__device__ __forceinline__ float3 sh_backward(int deg, int M, const float3 pos, const float3 campos,
-                                              const float* __restrict__ sh, const uint8_t* clamped,
-                                              const float3 dL_dcolor, float* __restrict__ dL_dsh) {
+__device__ __forceinline__ float3 sh_backward(int deg, const float3 pos, const float3 campos, const float* sh,
+                                              const uint8_t* clamped, const float3 dL_dcolor, float* dL_dsh) {
   const float3 dir_orig = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
   const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
   const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
@@ -300,10 +339,8 @@ __device__ __forceinline__ float3 sh_backward(int deg, int M, const float3 pos, 
   const int ncoef = (deg + 1) * (deg + 1);
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    if (k < M) {
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) dL_dsh[k * 3 + ch] = (k < ncoef) ? w[k] * dRGB[ch] : 0.f;
-    }
+    for (int ch = 0; ch < 3; ++ch) dL_dsh[k * 3 + ch] = (k < ncoef) ? w[k] * dRGB[ch] : 0.f;
   }
 
 #pragma unroll
@@ -374,10 +411,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
   dL_dmean2D[3 * idx + 0] = dm2.x;
   dL_dmean2D[3 * idx + 1] = dm2.y;
   dL_dmean2D[3 * idx + 2] = 0.f;
-  dL_dconic[4 * idx + 0] = dcon.x;
-  dL_dconic[4 * idx + 1] = dcon.y;
-  dL_dconic[4 * idx + 2] = 0.f;
-  dL_dconic[4 * idx + 3] = dcon.z;
+  reinterpret_cast<float4*>(dL_dconic)[idx] = make_float4(dcon.x, dcon.y, 0.f, dcon.z);
   dL_dopacity[idx] = dop;
   dL_dcolor[3 * idx + 0] = dcol.x;
   dL_dcolor[3 * idx + 1] = dcol.y;
@@ -389,8 +423,15 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
   float4 drot = make_float4(0, 0, 0, 0);
 
   if (!visible) {
-    if (dL_dsh)
-      for (int k = 0; k < M * 3; ++k) dL_dsh[(size_t)idx * M * 3 + k] = 0.f;
+    if (dL_dsh) {
+      float* dst = dL_dsh + (size_t)idx * M * 3;
+      if (M == 16) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int k = 0; k < M * 3; ++k) dst[k] = 0.f;
+      }
+    }
   } else {
     const float3 mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
     const float* cov3D = cov3D_precomp ? cov3D_precomp + 6 * idx : g.cov3D + 6 * idx;
@@ -463,17 +504,27 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
     // ---------------- SH colour (backward.cu:20-139, 383-385)
     if (shs) {
       const float3 cp = make_float3(cam_pos[0], cam_pos[1], cam_pos[2]);
-      const float3 dms = sh_backward(D, M, mean, cp, shs + (size_t)idx * M * 3, g.clamped + 3 * idx, dcol,
-                                     dL_dsh + (size_t)idx * M * 3);
+      float sh[48], dsh[48];
+      load_sh(shs, idx, M, (D + 1) * (D + 1), sh);
+      const float3 dms = sh_backward(D, mean, cp, sh, g.clamped + 3 * idx, dcol, dsh);
       dmean.x += dms.x;
       dmean.y += dms.y;
       dmean.z += dms.z;
+      float* dst = dL_dsh + (size_t)idx * M * 3;
+      if (M == 16) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+          reinterpret_cast<float4*>(dst)[i] = make_float4(dsh[4 * i], dsh[4 * i + 1], dsh[4 * i + 2], dsh[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 48; ++i)
+          if (i < M * 3) dst[i] = dsh[i];
+      }
     }
     // ---------------- 3D covariance -> scale / rotation (backward.cu:279-341)
     if (scales) {
       const float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
-      const float4 q = make_float4(rotations[4 * idx], rotations[4 * idx + 1], rotations[4 * idx + 2],
-                                   rotations[4 * idx + 3]);
+      const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
       const float r = q.x, x = q.y, y = q.z, z = q.w;
       Mat3 R;
       quat_to_R(q, R);
@@ -532,10 +583,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
   dL_dscale[3 * idx + 0] = dscale.x;
   dL_dscale[3 * idx + 1] = dscale.y;
   dL_dscale[3 * idx + 2] = dscale.z;
-  dL_drot[4 * idx + 0] = drot.x;
-  dL_drot[4 * idx + 1] = drot.y;
-  dL_drot[4 * idx + 2] = drot.z;
-  dL_drot[4 * idx + 3] = drot.w;
+  reinterpret_cast<float4*>(dL_drot)[idx] = drot;
 }
 
 cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s) {
@@ -549,8 +597,8 @@ cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s) {
   const float focal_x = a.W / (2.0f * a.tan_fovx);
   const int* radii = a.radii ? a.radii : g.radii;
   g_prof.begin(5, s);
-  render_bwd_kernel<<<T, 256, 0, s>>>(im.ranges, b.inst_geo, b.inst_attr, a.W, a.H, a.background, im.final_T,
-                                      im.n_contrib, a.dL_dpix, g.grad_acc);
+  render_bwd_kernel<<<T, 256, 0, s>>>(im.ranges, im.tile_order, b.inst_geo, b.inst_attr, a.W, a.H, a.background,
+                                      im.final_T, im.n_contrib, a.dL_dpix, g.grad_acc);
   g_prof.end(5, s);
   g_prof.begin(6, s);
   preprocess_bwd_kernel<<<(a.P + 127) / 128, 128, 0, s>>>(

@@ -27,108 +27,107 @@ namespace dgm {
 
 // =========================================================== preprocess ====
 // One thread per Gaussian (forward.cu:155-256).  Besides the reference outputs it
-// counts instances per tile (atomics on T counters) and clears the backward
-// accumulators.  Rectangles larger than 32 tiles are counted warp-cooperatively.
-__global__ void __launch_bounds__(256) preprocess_kernel(
-    int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
-    const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
-    const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
-    const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
-    int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int* __restrict__ radii_out,
-    GeomWS g, unsigned gx, unsigned gy, uint32_t* __restrict__ tile_counts, int prefiltered) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned lane = threadIdx.x & 31;
-  bool valid = idx < P;
-  uint2 rmin = make_uint2(0, 0), rmax = make_uint2(0, 0);
-  float3 p_view = make_float3(0, 0, 0);
+// clears the backward accumulators and tracks the depth range of the visible set.
+//
+// Binning = one MSD counting pass on (tile, depth bucket) + tiny sorts:
+//   count_kernel    hist[tile][bucket] += 1 per (Gaussian, tile) instance, bucket = linear
+//                   quantisation of the view depth into DEPTH_BUCKETS slots.  ~T*256 counters
+//                   -> no hot addresses (returning atomics on T counters serialise at ~64
+//                   cycles/op on the busiest tiles, ncu r1a)
+//   tile_scan_kernel  exclusive offsets of every (tile, bucket) block + tile ranges
+//   scatter_kernel  keys into their block (cursor = the offset table itself)
+//   tile_sort_pack_kernel  each block holds a handful of keys: one thread sorts one block;
+//                   a tile whose largest block is long falls back to a full bitonic sort.
+#define DEPTH_BUCKETS 256
 
-  if (valid) {
-    g.radii[idx] = 0;
-    if (radii_out) radii_out[idx] = 0;
-    g.tiles_touched[idx] = 0;
-    g.grad_acc[3 * idx + 0] = make_float4(0, 0, 0, 0);
-    g.grad_acc[3 * idx + 1] = make_float4(0, 0, 0, 0);
-    g.grad_acc[3 * idx + 2] = make_float4(0, 0, 0, 0);
-  }
-  float3 p_orig = make_float3(0, 0, 0);
-  float4 p_hom;
-  float p_w;
-  float3 p_proj = make_float3(0, 0, 0);
-  if (valid) {
-    p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
-    // near culling (auxiliary.h:139-164)
-    p_hom = xform4x4(p_orig, projmatrix);
-    p_w = 1.0f / (p_hom.w + 0.0000001f);
-    p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
-    p_view = xform4x3(p_orig, viewmatrix);
-    if (p_view.z <= 0.2f) {
-      if (prefiltered) {
-        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-        __trap();
-      }
-      valid = false;
+struct PreOut {
+  uint2 rmin, rmax;
+  uint32_t ntiles;
+};
+
+__device__ __forceinline__ bool preprocess_one(
+    int idx, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
+    const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
+    const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp, const float* viewmatrix,
+    const float* projmatrix, const float* cam_pos, int W, int H, float tan_fovx, float tan_fovy, float focal_x,
+    float focal_y, int* __restrict__ radii_out, const GeomWS& g, unsigned gx, unsigned gy, int prefiltered,
+    PreOut& o) {
+  g.radii[idx] = 0;
+  if (radii_out) radii_out[idx] = 0;
+  g.tiles_touched[idx] = 0;
+  g.grad_acc[3 * idx + 0] = make_float4(0, 0, 0, 0);
+  g.grad_acc[3 * idx + 1] = make_float4(0, 0, 0, 0);
+  g.grad_acc[3 * idx + 2] = make_float4(0, 0, 0, 0);
+  const float3 p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+  // near culling (auxiliary.h:139-164)
+  const float4 p_hom = xform4x4(p_orig, projmatrix);
+  const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+  const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+  const float3 p_view = xform4x3(p_orig, viewmatrix);
+  if (p_view.z <= 0.2f) {
+    if (prefiltered) {
+      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+      __trap();
     }
+    return false;
   }
-  float my_radius = 0.f;
-  float2 point_image = make_float2(0, 0);
-  float3 conic = make_float3(0, 0, 0);
-  if (valid) {
-    const float* cov3D;
-    if (cov3D_precomp != nullptr) {
-      cov3D = cov3D_precomp + idx * 6;
-    } else {
-      const float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
-      const float4 q = make_float4(rotations[4 * idx], rotations[4 * idx + 1], rotations[4 * idx + 2],
-                                   rotations[4 * idx + 3]);
-      cov3d_from_scale_rot(sc, scale_modifier, q, g.cov3D + idx * 6);
-      cov3D = g.cov3D + idx * 6;
-    }
-    EwaFrame fr;
-    ewa_frame(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, viewmatrix, fr);
-    const float3 cov = ewa_cov2d(fr);
-    // invert (EWA), forward.cu:217-221
-    const float det = (cov.x * cov.z - cov.y * cov.y);
-    if (det == 0.0f) {
-      valid = false;
-    } else {
-      const float det_inv = 1.f / det;
-      conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
-      // screen-space extent from the larger eigenvalue, forward.cu:227-235
-      const float mid = 0.5f * (cov.x + cov.z);
-      const float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
-      const float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
-      my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
-      point_image = make_float2(ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H));
-      tile_rect(point_image, my_radius, rmin, rmax, gx, gy);
-      if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) valid = false;
-    }
+  const float* cov3D;
+  if (cov3D_precomp != nullptr) {
+    cov3D = cov3D_precomp + idx * 6;
+  } else {
+    const float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
+    const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+    cov3d_from_scale_rot(sc, scale_modifier, q, g.cov3D + idx * 6);
+    cov3D = g.cov3D + idx * 6;
   }
-  uint32_t ntiles = 0;
-  if (valid) {
-    if (colors_precomp == nullptr) {
-      bool cl[3];
-      const float3 cp = make_float3(cam_pos[0], cam_pos[1], cam_pos[2]);
-      const float3 c = sh_to_rgb(D, p_orig, cp, shs + (size_t)idx * M * 3, cl);
-      g.clamped[3 * idx + 0] = cl[0];
-      g.clamped[3 * idx + 1] = cl[1];
-      g.clamped[3 * idx + 2] = cl[2];
-      g.rgb[3 * idx + 0] = c.x;
-      g.rgb[3 * idx + 1] = c.y;
-      g.rgb[3 * idx + 2] = c.z;
-    }
-    g.depths[idx] = p_view.z;
-    g.radii[idx] = my_radius;
-    if (radii_out) radii_out[idx] = my_radius;
-    g.means2D[idx] = point_image;
-    g.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, opacities[idx]);
-    ntiles = (rmax.y - rmin.y) * (rmax.x - rmin.x);
-    g.tiles_touched[idx] = ntiles;
+  EwaFrame fr;
+  ewa_frame(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, viewmatrix, fr);
+  const float3 cov = ewa_cov2d(fr);
+  // invert (EWA), forward.cu:217-221
+  const float det = (cov.x * cov.z - cov.y * cov.y);
+  if (det == 0.0f) return false;
+  const float det_inv = 1.f / det;
+  const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+  // screen-space extent from the larger eigenvalue, forward.cu:227-235
+  const float mid = 0.5f * (cov.x + cov.z);
+  const float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
+  const float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
+  const float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
+  const float2 point_image = make_float2(ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H));
+  tile_rect(point_image, my_radius, o.rmin, o.rmax, gx, gy);
+  if ((o.rmax.x - o.rmin.x) * (o.rmax.y - o.rmin.y) == 0) return false;
+  if (colors_precomp == nullptr) {
+    bool cl[3];
+    float sh[48];
+    load_sh(shs, idx, M, (D + 1) * (D + 1), sh);
+    const float3 cp = make_float3(cam_pos[0], cam_pos[1], cam_pos[2]);
+    const float3 c = sh_to_rgb(D, p_orig, cp, sh, cl);
+    g.clamped[3 * idx + 0] = cl[0];
+    g.clamped[3 * idx + 1] = cl[1];
+    g.clamped[3 * idx + 2] = cl[2];
+    g.rgb[3 * idx + 0] = c.x;
+    g.rgb[3 * idx + 1] = c.y;
+    g.rgb[3 * idx + 2] = c.z;
   }
-  // ---- per-tile instance counts
+  g.depths[idx] = p_view.z;
+  g.radii[idx] = my_radius;
+  if (radii_out) radii_out[idx] = my_radius;
+  g.means2D[idx] = point_image;
+  g.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, opacities[idx]);
+  o.ntiles = (o.rmax.y - o.rmin.y) * (o.rmax.x - o.rmin.x);
+  g.tiles_touched[idx] = o.ntiles;
+  return true;
+}
+
+// call f(tile, payload) once per tile of each lane's rectangle; rectangles larger than 32
+// tiles are spread over the whole warp (payload of the owning lane is broadcast)
+template <typename F>
+__device__ __forceinline__ void for_each_tile_warp(const uint2 rmin, const uint2 rmax, uint32_t ntiles, unsigned gx,
+                                                   unsigned lane, unsigned long long payload, F&& f) {
   const bool big = ntiles > 32;
-  if (valid && !big) {
+  if (ntiles && !big) {
     for (unsigned y = rmin.y; y < rmax.y; ++y)
-      for (unsigned x = rmin.x; x < rmax.x; ++x) atomicAdd(&tile_counts[y * gx + x], 1u);
+      for (unsigned x = rmin.x; x < rmax.x; ++x) f(y * gx + x, payload);
   }
   unsigned bigmask = __ballot_sync(0xffffffffu, big);
   while (bigmask) {
@@ -136,31 +135,149 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     bigmask &= bigmask - 1;
     const unsigned x0 = __shfl_sync(0xffffffffu, rmin.x, src), y0 = __shfl_sync(0xffffffffu, rmin.y, src);
     const unsigned x1 = __shfl_sync(0xffffffffu, rmax.x, src), y1 = __shfl_sync(0xffffffffu, rmax.y, src);
+    const unsigned long long pl = __shfl_sync(0xffffffffu, payload, src);
     const unsigned w = x1 - x0, n = w * (y1 - y0);
-    for (unsigned k = lane; k < n; k += 32) atomicAdd(&tile_counts[(y0 + k / w) * gx + (x0 + k % w)], 1u);
+    for (unsigned k = lane; k < n; k += 32) f((y0 + k / w) * gx + (x0 + k % w), pl);
   }
 }
 
-// ============================================================ tile scan ====
-// Exclusive scan of the per-tile counts -> ranges (rasterizer_impl.cu:116-138 writes
-// the same [start,end) pairs after its global sort).  Single CTA; T is a few thousand.
-__global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* __restrict__ tile_counts,
-                                                         uint2* __restrict__ ranges, int32_t* __restrict__ status,
-                                                         long long R_cap) {
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
-  __shared__ uint32_t s_max;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) {
-    s_carry = 0;
-    s_max = 0;
+__global__ void __launch_bounds__(256) preprocess_kernel(
+    int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
+    const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
+    const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
+    const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
+    int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int* __restrict__ radii_out,
+    GeomWS g, unsigned gx, unsigned gy, uint32_t* __restrict__ depth_range, uint32_t* __restrict__ scan_flags,
+    int32_t* __restrict__ status, int prefiltered) {
+  __shared__ float s_cam[36];
+  const unsigned tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid < 8) {  // state consumed by tile_scan_kernel, which runs after this grid
+    scan_flags[tid] = 0;
+    status[tid] = 0;
   }
+  if (tid < 16) s_cam[tid] = viewmatrix[tid];
+  else if (tid < 32) s_cam[tid] = projmatrix[tid - 16];
+  else if (tid < 35) s_cam[tid] = cam_pos[tid - 32];
+  __syncthreads();
+  const int idx = blockIdx.x * 256 + tid;
+  PreOut o;
+  o.rmin = o.rmax = make_uint2(0, 0);
+  o.ntiles = 0;
+  bool ok = false;
+  if (idx < P)
+    ok = preprocess_one(idx, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,
+                        colors_precomp, s_cam, s_cam + 16, s_cam + 32, W, H, tan_fovx, tan_fovy, focal_x, focal_y,
+                        radii_out, g, gx, gy, prefiltered, o);
+  // depth range of the visible Gaussians (positive floats order like their bit patterns);
+  // depth_range = { max of ~bits (i.e. the minimum), max of bits }, both zero-initialised
+  uint32_t dmax = ok ? __float_as_uint(g.depths[idx]) : 0u;
+  uint32_t dmin_inv = ok ? ~dmax : 0u;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, off));
+    dmin_inv = max(dmin_inv, __shfl_xor_sync(0xffffffffu, dmin_inv, off));
+  }
+  if ((tid & 31) == 0 && dmax) {
+    atomicMax(&depth_range[0], dmin_inv);
+    atomicMax(&depth_range[1], dmax);
+  }
+}
+
+// depth -> bucket; monotone non-decreasing in the depth (same code in count and scatter)
+struct DepthBuckets {
+  float dmin, scale;
+  __device__ __forceinline__ DepthBuckets(const uint32_t* depth_range) {
+    dmin = __uint_as_float(~depth_range[0]);
+    const float dmax = __uint_as_float(depth_range[1]);
+    scale = (dmax > dmin) ? (float)DEPTH_BUCKETS / (dmax - dmin) : 0.0f;
+  }
+  __device__ __forceinline__ unsigned of(float depth) const {
+    const float x = (depth - dmin) * scale;
+    return min((unsigned)(DEPTH_BUCKETS - 1), (unsigned)max(x, 0.0f));
+  }
+};
+
+// ================================================================ count ====
+__global__ void __launch_bounds__(256) count_kernel(int P, GeomWS g, uint32_t* __restrict__ hist,
+                                                    const uint32_t* __restrict__ depth_range, unsigned gx,
+                                                    unsigned gy) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31;
+  const DepthBuckets db(depth_range);
+  uint2 rmin = make_uint2(0, 0), rmax = make_uint2(0, 0);
+  uint32_t ntiles = 0;
+  unsigned long long bucket = 0;
+  if (idx < P) {
+    const int r = g.radii[idx];
+    if (r > 0) {
+      tile_rect(g.means2D[idx], r, rmin, rmax, gx, gy);
+      ntiles = (rmax.y - rmin.y) * (rmax.x - rmin.x);
+      bucket = db.of(g.depths[idx]);
+    }
+  }
+  for_each_tile_warp(rmin, rmax, ntiles, gx, lane, bucket, [&](unsigned t, unsigned long long b) {
+    atomicAdd(&hist[(size_t)t * DEPTH_BUCKETS + (unsigned)b], 1u);
+  });
+}
+
+// ============================================================ tile scan ====
+// hist[T, B] ((tile, depth bucket) counts) -> in place: exclusive prefix over the buckets of
+// each tile; then the last CTA to finish scans the T tile totals into ranges[t] =
+// [start, end) (what identifyTileRanges, rasterizer_impl.cu:116-138, derives from the
+// sorted keys), writes R / overflow into `status`, and orders the tiles by decreasing
+// list length (coarse, by power-of-two bucket) so the blend kernels start their longest
+// tiles first.  CTA = 32 tiles x 8 bucket groups.
+__global__ void __launch_bounds__(256) tile_scan_kernel(int T, uint32_t* __restrict__ hist,
+                                                        uint32_t* __restrict__ tile_total, uint2* __restrict__ ranges,
+                                                        uint32_t* __restrict__ tile_order,
+                                                        uint32_t* __restrict__ flags, int32_t* __restrict__ status,
+                                                        long long R_cap) {
+  __shared__ uint32_t s_part[8][33];
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_bucket[33];
+  __shared__ uint32_t s_carry, s_last;
+  const int tid = threadIdx.x;
+  {
+    const int tx = tid & 31, seg = tid >> 5;
+    const int t = blockIdx.x * 32 + tx;
+    const int r0 = seg * (DEPTH_BUCKETS / 8), r1 = r0 + DEPTH_BUCKETS / 8;
+    uint32_t* row = hist + (size_t)(t < T ? t : 0) * DEPTH_BUCKETS;
+    uint32_t sum = 0;
+    if (t < T) {
+#pragma unroll 8
+      for (int c = r0; c < r1; ++c) sum += row[c];
+    }
+    s_part[seg][tx] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int k = 0; k < seg; ++k) run += s_part[k][tx];
+    if (t < T) {
+#pragma unroll 8
+      for (int c = r0; c < r1; ++c) {
+        const uint32_t v = row[c];
+        row[c] = run;
+        run += v;
+      }
+      if (seg == 7) tile_total[t] = run;  // the last segment ends with the column total
+    }
+  }
+  // ---- last CTA done: scan of the column totals
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&flags[0], 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  if (tid < 33) s_bucket[tid] = 0;
   __syncthreads();
   uint32_t local_max = 0;
-  for (int base = 0; base < T; base += 1024) {
+  for (int base = 0; base < T; base += 256) {
     const int t = base + tid;
-    const uint32_t c = (t < T) ? tile_counts[t] : 0u;
+    const uint32_t c = (t < T) ? __ldcg(tile_total + t) : 0u;
     local_max = max(local_max, c);
+    if (t < T) atomicAdd(&s_bucket[c ? 32 - __clz(c) : 0], 1u);  // bucket b holds 2^(b-1) <= c < 2^b
     uint32_t v = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -170,42 +287,57 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* 
     if (lane == 31) s_warp[wid] = v;
     __syncthreads();
     if (wid == 0) {
-      uint32_t w = s_warp[lane];
+      uint32_t w = lane < 8 ? s_warp[lane] : 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
+      for (int o = 1; o < 8; o <<= 1) {
         const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
         if (lane >= o) w += n;
       }
-      s_warp[lane] = w;  // inclusive over warps
+      if (lane < 8) s_warp[lane] = w;
     }
     __syncthreads();
-    const uint32_t warp_off = (wid == 0) ? 0u : s_warp[wid - 1];
-    const uint32_t incl = s_carry + warp_off + v;
+    const uint32_t incl = s_carry + (wid ? s_warp[wid - 1] : 0u) + v;
     if (t < T) ranges[t] = c ? make_uint2(incl - c, incl) : make_uint2(0u, 0u);
     __syncthreads();
-    if (tid == 1023) s_carry = incl;
+    if (tid == 255) s_carry = incl;
     __syncthreads();
   }
-  atomicMax(&s_max, local_max);
-  __syncthreads();
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+  if (lane == 0) atomicMax(reinterpret_cast<unsigned*>(status + 2), local_max);
+  // tile order: longest bucket first
   if (tid == 0) {
+    uint32_t acc = 0;
+    for (int b = 32; b >= 0; --b) {
+      const uint32_t n = s_bucket[b];
+      s_bucket[b] = acc;
+      acc += n;
+    }
     status[0] = (int32_t)s_carry;
     status[1] = ((long long)s_carry > R_cap) ? 1 : 0;
-    status[2] = (int32_t)s_max;
+  }
+  __syncthreads();
+  for (int t = tid; t < T; t += 256) {
+    const uint32_t c = __ldcg(tile_total + t);
+    const uint32_t pos = atomicAdd(&s_bucket[c ? 32 - __clz(c) : 0], 1u);
+    tile_order[pos] = (uint32_t)t;
   }
 }
 
 // ============================================================== scatter ====
-// Emit one (depth bits << 32 | gaussian id) key per (Gaussian, tile) instance into the
-// tile's segment (role of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id is
-// implied by the segment, so the 64-bit word carries the gaussian id instead).
+// Emit one (depth bits << 32 | gaussian id) key per (Gaussian, tile) instance into its
+// (tile, bucket) block (role of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id
+// is implied by the segment, so the 64-bit word carries the gaussian id instead).  The
+// offset table doubles as the cursor: afterwards hist[t][b] is the END of block b.
 __global__ void __launch_bounds__(256) scatter_kernel(int P, GeomWS g, const uint2* __restrict__ ranges,
-                                                      uint32_t* __restrict__ tile_fill,
+                                                      uint32_t* __restrict__ hist,
+                                                      const uint32_t* __restrict__ depth_range,
                                                       unsigned long long* __restrict__ keys, unsigned gx, unsigned gy,
                                                       const int32_t* __restrict__ status) {
   if (status[1]) return;  // overflow: nothing may be written
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
+  const DepthBuckets db(depth_range);
   uint2 rmin = make_uint2(0, 0), rmax = make_uint2(0, 0);
   unsigned long long key = 0;
   uint32_t ntiles = 0;
@@ -217,76 +349,60 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, GeomWS g, const uin
       key = ((unsigned long long)__float_as_uint(g.depths[idx]) << 32) | (unsigned)idx;
     }
   }
-  const bool big = ntiles > 32;
-  if (ntiles && !big) {
-    for (unsigned y = rmin.y; y < rmax.y; ++y)
-      for (unsigned x = rmin.x; x < rmax.x; ++x) {
-        const unsigned t = y * gx + x;
-        const uint32_t slot = atomicAdd(&tile_fill[t], 1u);
-        keys[ranges[t].x + slot] = key;
-      }
-  }
-  unsigned bigmask = __ballot_sync(0xffffffffu, big);
-  while (bigmask) {
-    const int src = __ffs(bigmask) - 1;
-    bigmask &= bigmask - 1;
-    const unsigned x0 = __shfl_sync(0xffffffffu, rmin.x, src), y0 = __shfl_sync(0xffffffffu, rmin.y, src);
-    const unsigned x1 = __shfl_sync(0xffffffffu, rmax.x, src), y1 = __shfl_sync(0xffffffffu, rmax.y, src);
-    const unsigned long long k64 = __shfl_sync(0xffffffffu, key, src);
-    const unsigned w = x1 - x0, n = w * (y1 - y0);
-    for (unsigned k = lane; k < n; k += 32) {
-      const unsigned t = (y0 + k / w) * gx + (x0 + k % w);
-      const uint32_t slot = atomicAdd(&tile_fill[t], 1u);
-      keys[ranges[t].x + slot] = k64;
-    }
-  }
+  for_each_tile_warp(rmin, rmax, ntiles, gx, lane, key, [&](unsigned t, unsigned long long k64) {
+    const unsigned b = db.of(__uint_as_float((unsigned)(k64 >> 32)));
+    const uint32_t pos = ranges[t].x + atomicAdd(&hist[(size_t)t * DEPTH_BUCKETS + b], 1u);
+    keys[pos] = k64;
+  });
 }
 
 // ======================================================= tile sort+pack ====
 // One CTA per tile: sort the segment by (depth bits, gaussian id) with a normalised
 // bitonic network (all comparators ascending, so virtual +inf padding never moves and
 // any length works), then write point_list and the packed blend records.
-#define SORT_SMEM_KEYS 6144  // 48 KB static shared memory
+#define SORT_SMEM_KEYS 6016  // 47 KB static shared memory
+
+__device__ __forceinline__ void cmpswap(unsigned long long* a, uint32_t lo, uint32_t hi, uint32_t n) {
+  if (hi < n) {
+    const unsigned long long x = a[lo], y = a[hi];
+    if (x > y) {
+      a[lo] = y;
+      a[hi] = x;
+    }
+  }
+}
 
 __device__ __forceinline__ void bitonic_sort_any(unsigned long long* a, uint32_t n, uint32_t tid, uint32_t nthreads) {
-  uint32_t m = 1;
-  while (m < n) m <<= 1;
-  for (uint32_t k = 2; k <= m; k <<= 1) {
-    const uint32_t hk = k >> 1;
-    // mirror step
-    for (uint32_t i = tid; i < (m >> 1); i += nthreads) {
-      const uint32_t blk = i / hk, off = i - blk * hk;
-      const uint32_t lo = blk * k + off, hi = blk * k + k - 1 - off;
-      if (hi < n) {
-        const unsigned long long x = a[lo], y = a[hi];
-        if (x > y) {
-          a[lo] = y;
-          a[hi] = x;
-        }
-      }
+  if (n < 2) return;
+  const uint32_t lm = 32 - __clz(n - 1);  // m = 1 << lm = next power of two >= n
+  const uint32_t half = 1u << (lm - 1);
+  for (uint32_t lk = 1; lk <= lm; ++lk) {  // merge size k = 1 << lk
+    const uint32_t hk = 1u << (lk - 1);
+    // mirror step: i -> (block base + off, block base + k - 1 - off)
+    for (uint32_t i = tid; i < half; i += nthreads) {
+      const uint32_t off = i & (hk - 1), base = (i >> (lk - 1)) << lk;
+      cmpswap(a, base + off, base + (hk << 1) - 1 - off, n);
     }
     __syncthreads();
     for (uint32_t j = hk >> 1; j >= 1; j >>= 1) {
-      for (uint32_t i = tid; i < (m >> 1); i += nthreads) {
-        const uint32_t lo = (i / j) * (j << 1) + (i % j), hi = lo + j;
-        if (hi < n) {
-          const unsigned long long x = a[lo], y = a[hi];
-          if (x > y) {
-            a[lo] = y;
-            a[hi] = x;
-          }
-        }
+      for (uint32_t i = tid; i < half; i += nthreads) {
+        const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        cmpswap(a, lo, lo + j, n);
       }
       __syncthreads();
     }
   }
 }
 
+#define BLOCK_SORT_MAX 48  // longest (tile, bucket) block one thread sorts by insertion
+
 __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __restrict__ ranges,
-                                                             unsigned long long* __restrict__ keys, GeomWS g,
+                                                             unsigned long long* __restrict__ keys,
+                                                             const uint32_t* __restrict__ hist, GeomWS g,
                                                              const float* __restrict__ colors_precomp, BinWS b,
                                                              const int32_t* __restrict__ status) {
   __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
+  __shared__ uint32_t s_maxblock;
   if (status[1]) return;
   const uint2 range = ranges[blockIdx.x];
   const uint32_t n = range.y - range.x;
@@ -298,10 +414,34 @@ __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __rest
     for (uint32_t i = tid; i < n; i += 256) s_keys[i] = seg[i];
     a = s_keys;
   } else {
-    a = seg;  // rare: sort the segment in place in global memory (L2-resident)
+    a = seg;  // rare: work on the segment in place in global memory (L2-resident)
   }
+  // block tid of this tile: [bstart, bend) relative to the segment (scatter left the block END in hist)
+  const uint32_t* row = hist + (size_t)blockIdx.x * DEPTH_BUCKETS;
+  const uint32_t bend = row[tid];
+  const uint32_t bstart = tid ? row[tid - 1] : 0u;
+  if (tid == 0) s_maxblock = 0;
   __syncthreads();
-  bitonic_sort_any(a, n, tid, 256);
+  uint32_t mx = bend - bstart;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) atomicMax(&s_maxblock, mx);
+  __syncthreads();
+  if (s_maxblock <= BLOCK_SORT_MAX) {
+    // the buckets are already in depth order: sort each short block on its own
+    for (uint32_t i = bstart + 1; i < bend; ++i) {
+      const unsigned long long key = a[i];
+      uint32_t j = i;
+      while (j > bstart && a[j - 1] > key) {
+        a[j] = a[j - 1];
+        --j;
+      }
+      a[j] = key;
+    }
+    __syncthreads();
+  } else {
+    bitonic_sort_any(a, n, tid, 256);
+  }
   const float* colors = colors_precomp ? colors_precomp : g.rgb;
   for (uint32_t i = tid; i < n; i += 256) {
     const unsigned long long k = a[i];
@@ -336,6 +476,7 @@ __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __rest
 #define RB 256  // records per batch (== reference BLOCK_SIZE staging granularity)
 
 __global__ void __launch_bounds__(256) render_fwd_kernel(const uint2* __restrict__ ranges,
+                                                         const uint32_t* __restrict__ tile_order,
                                                          const float4* __restrict__ inst_geo,
                                                          const float4* __restrict__ inst_attr, int W, int H,
                                                          const float* __restrict__ bg_color,
@@ -347,7 +488,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const uint2* __restrict
   __shared__ __align__(8) uint64_t s_bar[2];
 
   const unsigned gx = (W + TILE_X - 1) / TILE_X;
-  const unsigned tile = blockIdx.x;
+  const unsigned tile = tile_order[blockIdx.x];  // longest lists first
   const unsigned tx = tile % gx, ty = tile / gx;
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // warp -> 8x4 block inside the tile; lane -> pixel inside the block
@@ -357,6 +498,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const uint2* __restrict
   const uint32_t pix_id = W * py + px;
   const float pixfx = (float)px, pixfy = (float)py;
   const float bx0 = (float)wx0, bx1 = (float)(wx0 + 7), by0 = (float)wy0, by1 = (float)(wy0 + 3);
+  const float2 npx2 = make_float2(-pixfx, -pixfx), npy2 = make_float2(-pixfy, -pixfy);
 
   uint2 range = ranges[tile];
   if (status[1]) range = make_uint2(0, 0);
@@ -412,32 +554,51 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const uint2* __restrict
       }
       keep[k] = __ballot_sync(0xffffffffu, kp);
     }
-    // ---- blend the survivors front to back
+    // ---- blend the survivors front to back, two records per iteration: the quadratic
+    // form of both is evaluated with packed fp32x2 instructions (FADD2/FMUL2/FFMA2, new on
+    // sm_100), the order-dependent transmittance update stays scalar.  The operation
+    // sequence (which product is fused into which FMA) is the one nvcc emits for the
+    // reference's renderCUDA (forward.cu:330-352; see profiles/ref_render_fwd_sass.txt),
+    // written with explicit-rounding intrinsics so it cannot be re-associated.
 #pragma unroll
     for (int k = 0; k < RB / 32; ++k) {
       unsigned mask = keep[k];
       if (mask == 0) continue;
       if (__all_sync(0xffffffffu, done)) break;
       while (mask) {
-        const int bit = __ffs(mask) - 1;
+        const int bA = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int j = k * 32 + bit;
-        const float4 ge = s_geo[st][j];
-        const float4 con_o = s_attr[st][2 * j];
-        const float4 col = s_attr[st][2 * j + 1];
-        if (!done) {
-          const float dx = ge.x - pixfx, dy = ge.y - pixfy;
-          const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
-          if (!(power > 0.0f)) {
-            const float alpha = min(0.99f, con_o.w * expf(power));
+        const bool two = mask != 0;
+        const int bB = two ? __ffs(mask) - 1 : bA;
+        mask &= mask - 1;  // no-op when mask is already 0
+        const int jA = k * 32 + bA, jB = k * 32 + bB;
+        const float4 geA = s_geo[st][jA], geB = s_geo[st][jB];
+        const float4 coA = s_attr[st][2 * jA], coB = s_attr[st][2 * jB];
+        const float2 dx = __fadd2_rn(make_float2(geA.x, geB.x), npx2);
+        const float2 dy = __fadd2_rn(make_float2(geA.y, geB.y), npy2);
+        float2 m1 = __fmul2_rn(dy, make_float2(coA.z, coB.z));
+        const float2 m2 = __fmul2_rn(dx, make_float2(coA.x, coB.x));
+        m1 = __fmul2_rn(dy, m1);
+        const float2 sq = __ffma2_rn(dx, m2, m1);
+        float2 m3 = __fmul2_rn(dx, make_float2(coA.y, coB.y));
+        m3 = __fmul2_rn(dy, m3);
+        const float2 npow = __ffma2_rn(sq, make_float2(0.5f, 0.5f), m3);  // = -power (exactly)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float np = q ? npow.y : npow.x;
+          const float opac = q ? coB.w : coA.w;
+          const int j = q ? jB : jA;
+          if ((q == 0 || two) && !done && !(np < 0.0f)) {  // reference: if (power > 0) continue
+            const float alpha = fminf(0.99f, __fmul_rn(opac, expf(-np)));
             if (!(alpha < 1.0f / 255.0f)) {
-              const float test_T = T * (1 - alpha);
+              const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
               if (test_T < 0.0001f) {
                 done = true;
               } else {
-                C0 += col.x * alpha * T;
-                C1 += col.y * alpha * T;
-                C2 += col.z * alpha * T;
+                const float4 col = s_attr[st][2 * j + 1];
+                C0 = __fmaf_rn(T, __fmul_rn(alpha, col.x), C0);
+                C1 = __fmaf_rn(T, __fmul_rn(alpha, col.y), C1);
+                C2 = __fmaf_rn(T, __fmul_rn(alpha, col.z), C2);
                 T = test_T;
                 last_contributor = base + j + 1;
               }
@@ -478,29 +639,31 @@ cudaError_t launch_forward(const FwdArgs& a, cudaStream_t s) {
   BinWS b = BinWS::from((char*)a.binning_ws, (size_t)a.R_cap);
   const float focal_y = a.H / (2.0f * a.tan_fovy);
   const float focal_x = a.W / (2.0f * a.tan_fovx);
-  cudaMemsetAsync(im.tile_counts, 0, im.zero_bytes, s);
-  if (a.P > 0) {
-    g_prof.begin(0, s);
-    preprocess_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(
-        a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations, a.opacities, a.shs, a.cov3D_precomp,
-        a.colors_precomp, a.viewmatrix, a.projmatrix, a.cam_pos, a.W, a.H, a.tan_fovx, a.tan_fovy, focal_x, focal_y,
-        a.radii, g, gx, gy, im.tile_counts, a.prefiltered);
-    g_prof.end(0, s);
-  }
+  const int pblocks = (a.P + 255) / 256;
+  // (tile, bucket) counters + the two depth-range words that follow them
+  cudaMemsetAsync(im.hist, 0, sizeof(uint32_t) * ((size_t)T * DEPTH_BUCKETS + 8), s);
+  g_prof.begin(0, s);
+  preprocess_kernel<<<pblocks, 256, 0, s>>>(
+      a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations, a.opacities, a.shs, a.cov3D_precomp,
+      a.colors_precomp, a.viewmatrix, a.projmatrix, a.cam_pos, a.W, a.H, a.tan_fovx, a.tan_fovy, focal_x, focal_y,
+      a.radii, g, gx, gy, im.depth_range, im.scan_flags, a.status, a.prefiltered);
+  g_prof.end(0, s);
+  g_prof.begin(7, s);
+  count_kernel<<<pblocks, 256, 0, s>>>(a.P, g, im.hist, im.depth_range, gx, gy);
+  g_prof.end(7, s);
   g_prof.begin(1, s);
-  tile_scan_kernel<<<1, 1024, 0, s>>>(T, im.tile_counts, im.ranges, a.status, (long long)a.R_cap);
+  tile_scan_kernel<<<(T + 31) / 32, 256, 0, s>>>(T, im.hist, im.tile_total, im.ranges, im.tile_order, im.scan_flags,
+                                                 a.status, (long long)a.R_cap);
   g_prof.end(1, s);
-  if (a.P > 0) {
-    g_prof.begin(2, s);
-    scatter_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, g, im.ranges, im.tile_fill, b.keys, gx, gy, a.status);
-    g_prof.end(2, s);
-    g_prof.begin(3, s);
-    tile_sort_pack_kernel<<<T, 256, 0, s>>>(im.ranges, b.keys, g, a.colors_precomp, b, a.status);
-    g_prof.end(3, s);
-  }
+  g_prof.begin(2, s);
+  scatter_kernel<<<pblocks, 256, 0, s>>>(a.P, g, im.ranges, im.hist, im.depth_range, b.keys, gx, gy, a.status);
+  g_prof.end(2, s);
+  g_prof.begin(3, s);
+  tile_sort_pack_kernel<<<T, 256, 0, s>>>(im.ranges, b.keys, im.hist, g, a.colors_precomp, b, a.status);
+  g_prof.end(3, s);
   g_prof.begin(4, s);
-  render_fwd_kernel<<<T, 256, 0, s>>>(im.ranges, b.inst_geo, b.inst_attr, a.W, a.H, a.background, im.final_T,
-                                      im.n_contrib, a.out_color, a.status);
+  render_fwd_kernel<<<T, 256, 0, s>>>(im.ranges, im.tile_order, b.inst_geo, b.inst_attr, a.W, a.H, a.background,
+                                      im.final_T, im.n_contrib, a.out_color, a.status);
   g_prof.end(4, s);
   return cudaGetLastError();
 }

@@ -204,4 +204,27 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 pos, const flo
   return make_float3(res[0], res[1], res[2]);
 }
 
+// this Gaussian's SH coefficients -> registers (only the first ncoef*3 values are valid)
+__device__ __forceinline__ void load_sh(const float* __restrict__ shs, size_t idx, int M, int ncoef, float* s) {
+  const float* src = shs + idx * (size_t)M * 3;
+  if (M == 16) {  // 192-byte records: 16-byte aligned vector loads, all independent
+    const float4* v = reinterpret_cast<const float4*>(src);
+    const int nv = (ncoef * 3 + 3) >> 2;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      if (i < nv) {
+        const float4 q = __ldg(v + i);
+        s[4 * i + 0] = q.x;
+        s[4 * i + 1] = q.y;
+        s[4 * i + 2] = q.z;
+        s[4 * i + 3] = q.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 48; ++i)
+      if (i < ncoef * 3) s[i] = __ldg(src + i);
+  }
+}
+
 }  // namespace dgm

@@ -30,6 +30,7 @@ if _root not in sys.path:
 import _dgm_lib  # noqa: E402
 
 _ST_WORDS = 8
+_SYNC = os.environ.get("DGMESH_B200_SYNC", "0") == "1"
 
 
 def _f32c(t, name):
@@ -46,25 +47,45 @@ class _Sizing:
     """High-water-mark capacity of the (Gaussian, tile) instance workspace per problem shape."""
     hint = {}       # (device, P, W, H) -> R capacity
     pending = []    # [(event, pinned status, key, R_cap)] forwards whose status was not read yet
+    free = []       # recycled (event, pinned buffer) pairs
+
+    @classmethod
+    def watch(cls, status, key, cap):
+        """Queue an asynchronous read-back of a forward's status block (no host sync)."""
+        if cls.free:
+            ev, host = cls.free.pop()
+        else:
+            ev, host = torch.cuda.Event(), torch.empty((_ST_WORDS,), dtype=torch.int32, pin_memory=True)
+        host.copy_(status, non_blocking=True)
+        ev.record()
+        cls.pending.append((ev, host, key, cap))
 
     @classmethod
     def poll(cls, block=False):
+        if not cls.pending:
+            return
         still = []
-        for ev, host, key, cap in cls.pending:
+        err = None
+        for item in cls.pending:
+            ev, host, key, cap = item
             if block:
                 ev.synchronize()
-            if ev.query():
+            if block or ev.query():
                 R, ovf = int(host[0]), int(host[1])
-                cls.hint[key] = max(cls.hint.get(key, 0), _grow(R))
+                g = _grow(R)
+                if g > cls.hint.get(key, 0):
+                    cls.hint[key] = g
                 if ovf:
-                    cls.pending = []
-                    raise _dgm_lib.DgmError(
-                        f"rasterizer instance workspace overflowed in an earlier forward (R={R} > capacity {cap}); "
-                        "that render was background-only. Capacity has been raised; re-run the step "
-                        "(or set DGMESH_B200_SYNC=1 for exact sizing with a host sync).")
+                    err = (R, cap)
+                cls.free.append((ev, host))
             else:
-                still.append((ev, host, key, cap))
+                still.append(item)
         cls.pending = still
+        if err is not None:
+            raise _dgm_lib.DgmError(
+                f"rasterizer instance workspace overflowed in an earlier forward (R={err[0]} > capacity {err[1]}); "
+                "that render was background-only. Capacity has been raised; re-run the step "
+                "(or set DGMESH_B200_SYNC=1 for exact sizing with a host sync).")
 
 
 def _round_cap(c):
@@ -81,55 +102,85 @@ def _cap_from_bytes(nbytes):
     return (int(nbytes) - 128) // 60
 
 
+_ws_sizes = {}
+
+
+def _sizes(P, W, H, R_cap):
+    k = (P, W, H, R_cap)
+    v = _ws_sizes.get(k)
+    if v is None:
+        gb, bb, ib = _dgm_lib.c_size_t(), _dgm_lib.c_size_t(), _dgm_lib.c_size_t()
+        _dgm_lib.check(_dgm_lib.lib().dgr_workspace_sizes(P, W, H, R_cap, gb, bb, ib), "dgr_workspace_sizes")
+        r = lambda x: (x + 511) // 512 * 512  # noqa: E731
+        v = (gb.value, bb.value, ib.value, r(gb.value), r(bb.value), r(ib.value))
+        if len(_ws_sizes) > 64:
+            _ws_sizes.clear()
+        _ws_sizes[k] = v
+    return v
+
+
+class _Workspace:
+    """geom | binning | img | status carved from ONE device allocation (the three opaque buffers
+    of the reference, dgr/rasterize_points.cu:68-78, kept together for the backward pass)."""
+    __slots__ = ("buf", "geom", "binning", "img", "status", "gb", "bb", "ib", "R_cap")
+
+    def __init__(self, P, W, H, R_cap, dev):
+        gb, bb, ib, ga, ba, ia = _sizes(P, W, H, R_cap)
+        self.buf = torch.empty((ga + ba + ia + 64,), dtype=torch.uint8, device=dev)
+        base = self.buf.data_ptr()
+        self.geom, self.binning, self.img, self.status = base, base + ga, base + ga + ba, base + ga + ba + ia
+        self.gb, self.bb, self.ib, self.R_cap = gb, bb, ib, R_cap
+
+    def status_tensor(self):
+        return self.buf[-64:-32].view(torch.int32)
+
+    # the reference-style separate byte tensors (views, no copies)
+    def split(self):
+        o1 = self.binning - self.geom
+        o2 = self.img - self.geom
+        return self.buf[:self.gb], self.buf[o1:o1 + self.bb], self.buf[o2:o2 + self.ib]
+
+
 def _raw_forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
                  projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered, R_cap):
-    """One enqueue of dgr_forward.  Returns (color, radii, geom, binning, img, status)."""
+    """One enqueue of dgr_forward.  Returns (color, radii, workspace)."""
     lib = _dgm_lib.lib()
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise ValueError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
     dev = means3D.device
     P = means3D.shape[0]
     M = int(sh.shape[1]) if (sh is not None and sh.numel() != 0) else 0
-    gb, bb, ib = _dgm_lib.c_size_t(), _dgm_lib.c_size_t(), _dgm_lib.c_size_t()
-    _dgm_lib.check(lib.dgr_workspace_sizes(P, W, H, R_cap, gb, bb, ib), "dgr_workspace_sizes")
+    ws = _Workspace(P, W, H, R_cap, dev)
     color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
-    geom = torch.empty((gb.value,), dtype=torch.uint8, device=dev)
-    binning = torch.empty((bb.value,), dtype=torch.uint8, device=dev)
-    img = torch.empty((ib.value,), dtype=torch.uint8, device=dev)
-    status = torch.empty((_ST_WORDS,), dtype=torch.int32, device=dev)
     p = _dgm_lib.ptr
     rc = lib.dgr_forward(P, degree, M, p(bg), W, H, p(means3D), p(sh), p(colors), p(opacity), p(scales),
                          float(scale_modifier), p(rotations), p(cov3D_precomp), p(viewmatrix), p(projmatrix),
                          p(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), p(color), p(radii),
-                         p(geom), gb.value, p(binning), bb.value, R_cap, p(img), ib.value, p(status),
+                         ws.geom, ws.gb, ws.binning, ws.bb, R_cap, ws.img, ws.ib, ws.status,
                          _dgm_lib.stream_ptr())
     _dgm_lib.check(rc, "dgr_forward")
-    return color, radii, geom, binning, img, status
+    return color, radii, ws
 
 
 def _forward_sized(args_fn, key, sync):
-    """Run the forward with a capacity policy.  args_fn(R_cap) enqueues and returns the tuple."""
+    """Run the forward with a capacity policy.  args_fn(R_cap) enqueues and returns (color, radii, ws)."""
     _Sizing.poll()
     cap = _Sizing.hint.get(key)
     if cap is None or sync:
         # first call for this shape (or strict mode): size exactly, one host sync
         cap0 = cap if cap is not None else _round_cap(max(4 * key[1], 1 << 18))
         out = args_fn(cap0)
-        st = out[-1].cpu()
+        st = out[2].status_tensor().cpu()
         R = int(st[0])
         _Sizing.hint[key] = max(_Sizing.hint.get(key, 0), _grow(R))
         if int(st[1]):
             cap0 = _Sizing.hint[key]
             out = args_fn(cap0)
-        return out, cap0, R
+        return out, R
     out = args_fn(cap)
-    host = torch.empty((_ST_WORDS,), dtype=torch.int32, pin_memory=True)
-    host.copy_(out[-1], non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record()
-    _Sizing.pending.append((ev, host, key, cap))
-    return out, cap, None
+    _Sizing.watch(out[2].status_tensor(), key, cap)
+    return out, None
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
@@ -146,62 +197,69 @@ class _RasterizeGaussians(torch.autograd.Function):
         means3D = _f32c(means3D, "means3D")
         if means3D is None:
             raise ValueError("means3D must have dimensions (num_points, 3)")
-        t = dict(bg=_f32c(rs.bg, "bg"), sh=_f32c(sh, "sh"), colors=_f32c(colors_precomp, "colors_precomp"),
-                 opac=_f32c(opacities, "opacities"), scales=_f32c(scales, "scales"),
-                 rots=_f32c(rotations, "rotations"), cov=_f32c(cov3Ds_precomp, "cov3D_precomp"),
-                 view=_f32c(rs.viewmatrix, "viewmatrix"), proj=_f32c(rs.projmatrix, "projmatrix"),
-                 campos=_f32c(rs.campos, "campos"))
+        t = (_f32c(rs.bg, "bg"), _f32c(sh, "sh"), _f32c(colors_precomp, "colors_precomp"),
+             _f32c(opacities, "opacities"), _f32c(scales, "scales"), _f32c(rotations, "rotations"),
+             _f32c(cov3Ds_precomp, "cov3D_precomp"), _f32c(rs.viewmatrix, "viewmatrix"),
+             _f32c(rs.projmatrix, "projmatrix"), _f32c(rs.campos, "campos"))
+        bg, sh_, col, opac, sc, rot, cov, view, proj, campos = t
         H, W = int(rs.image_height), int(rs.image_width)
         key = (means3D.device.index, means3D.shape[0], W, H)
 
         def run(R_cap):
-            return _raw_forward(t["bg"], means3D, t["colors"], t["opac"], t["scales"], t["rots"], rs.scale_modifier,
-                                t["cov"], t["view"], t["proj"], rs.tanfovx, rs.tanfovy, H, W, t["sh"], rs.sh_degree,
-                                t["campos"], rs.prefiltered, R_cap)
+            return _raw_forward(bg, means3D, col, opac, sc, rot, rs.scale_modifier, cov, view, proj, rs.tanfovx,
+                                rs.tanfovy, H, W, sh_, rs.sh_degree, campos, rs.prefiltered, R_cap)
 
-        sync = bool(rs.debug) or os.environ.get("DGMESH_B200_SYNC", "0") == "1"
-        (color, radii, geom, binning, img, status), cap, _ = _forward_sized(run, key, sync)
+        sync = bool(rs.debug) or _SYNC
+        (color, radii, ws), _ = _forward_sized(run, key, sync)
         ctx.raster_settings = rs
-        ctx.R_cap = cap
+        ctx.ws = ws
+        ctx.R_cap = ws.R_cap
         ctx.tensors = t
-        ctx.save_for_backward(means3D, radii, geom, binning, img, status)
+        ctx.has_m2d = means2D is not None
+        ctx.save_for_backward(means3D, radii)
         ctx.mark_non_differentiable(radii)
         return color, radii
 
     @staticmethod
     def backward(ctx, grad_out_color, _):
         rs = ctx.raster_settings
-        t = ctx.tensors
-        means3D, radii, geom, binning, img, status = ctx.saved_tensors
+        bg, sh, col, opac, sc, rot, cov, view, proj, campos = ctx.tensors
+        means3D, radii = ctx.saved_tensors
+        ws = ctx.ws
         _Sizing.poll(block=True)  # the forward must not have overflowed (raises otherwise)
         lib = _dgm_lib.lib()
         P = means3D.shape[0]
         H, W = int(rs.image_height), int(rs.image_width)
-        sh = t["sh"]
         M = int(sh.shape[1]) if sh is not None else 0
-        dev = means3D.device
-        f = dict(dtype=torch.float32, device=dev)
-        g_m2d = torch.empty((P, 3), **f)
-        g_conic = torch.empty((P, 2, 2), **f)
-        g_opac = torch.empty((P, 1), **f)
-        g_col = torch.empty((P, 3), **f)
-        g_m3d = torch.empty((P, 3), **f)
-        g_cov = torch.empty((P, 6), **f)
-        g_sh = torch.empty((P, M, 3), **f)
-        g_scale = torch.empty((P, 3), **f)
-        g_rot = torch.empty((P, 4), **f)
+        # all nine gradients in one allocation (each sub-buffer 16-byte aligned for vector stores):
+        # m2d[P,3] conic[P,4] opac[P] col[P,3] m3d[P,3] cov[P,6] scale[P,3] rot[P,4] sh[P,M,3]
+        offs, o = [], 0
+        for w in (3, 4, 1, 3, 3, 6, 3, 4, 3 * M):
+            offs.append(o)
+            o = (o + P * w + 3) // 4 * 4
+        flat = torch.empty((max(o, 1),), dtype=torch.float32, device=means3D.device)
+        base = flat.data_ptr()
+        ptrs = [base + 4 * x for x in offs]
+
+        def view(i, *shape):
+            n = 1
+            for d in shape:
+                n *= d
+            return flat[offs[i]:offs[i] + n].view(*shape)
+
         dpix = _f32c(grad_out_color, "grad_out_color")
         p = _dgm_lib.ptr
-        rc = lib.dgr_backward(P, rs.sh_degree, M, p(t["bg"]), W, H, p(means3D), p(sh), p(t["colors"]),
-                              p(t["scales"]), float(rs.scale_modifier), p(t["rots"]), p(t["cov"]), p(t["view"]),
-                              p(t["proj"]), p(t["campos"]), float(rs.tanfovx), float(rs.tanfovy), p(radii),
-                              p(geom), p(binning), ctx.R_cap, p(img), p(dpix), p(g_m2d), p(g_conic), p(g_opac),
-                              p(g_col), p(g_m3d), p(g_cov), p(g_sh), p(g_scale), p(g_rot), _dgm_lib.stream_ptr())
+        rc = lib.dgr_backward(P, rs.sh_degree, M, p(bg), W, H, p(means3D), p(sh), p(col), p(sc),
+                              float(rs.scale_modifier), p(rot), p(cov), p(view), p(proj), p(campos),
+                              float(rs.tanfovx), float(rs.tanfovy), p(radii), ws.geom, ws.binning, ws.R_cap, ws.img,
+                              p(dpix), ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5],
+                              ptrs[8] if M else None, ptrs[6], ptrs[7], _dgm_lib.stream_ptr())
         _dgm_lib.check(rc, "dgr_backward")
         # same ordering as the reference (:143-153)
-        return (g_m3d, g_m2d, g_sh if sh is not None else None, g_col if t["colors"] is not None else None, g_opac,
-                g_scale if t["scales"] is not None else None, g_rot if t["rots"] is not None else None,
-                g_cov if t["cov"] is not None else None, None)
+        return (view(4, P, 3), view(0, P, 3) if ctx.has_m2d else None, view(8, P, M, 3) if sh is not None else None,
+                view(3, P, 3) if col is not None else None, view(2, P, 1),
+                view(6, P, 3) if sc is not None else None, view(7, P, 4) if rot is not None else None,
+                view(5, P, 6) if cov is not None else None, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -274,9 +332,10 @@ class _CCompat:
             return _raw_forward(bg_, m3, col, op, sc, ro, scale_modifier, cov, view, proj, tan_fovx, tan_fovy,
                                 int(image_height), int(image_width), sh_, degree, cam, prefiltered, R_cap)
 
-        (color, radii, geom, binning, img, status), cap, R = _forward_sized(run, key, True)
-        # the three opaque byte tensors carry everything backward needs (capacity is implied by
-        # the size of the binning buffer)
+        (color, radii, ws), R = _forward_sized(run, key, True)
+        # the three opaque byte tensors (views of one allocation) carry everything backward needs;
+        # the capacity is implied by the size of the binning buffer
+        geom, binning, img = ws.split()
         return R, color, radii, geom, binning, img
 
     @staticmethod
@@ -323,10 +382,11 @@ class _CCompat:
 _C = _CCompat()
 
 
-def export_state(P, W, H, R_cap, geom, binning, img, R):
+def export_state(P, W, H, ws, R):
     """Parity-test helper: reference-visible intermediate state of a forward as a dict of tensors."""
     lib = _dgm_lib.lib()
-    dev = geom.device
+    dev = ws.buf.device
+    R_cap = ws.R_cap
     T = ((W + 15) // 16) * ((H + 15) // 16)
     o = dict(
         depths=torch.zeros(P, device=dev), means2D=torch.zeros(P, 2, device=dev),
@@ -338,7 +398,7 @@ def export_state(P, W, H, R_cap, geom, binning, img, R):
         ranges=torch.zeros(T, 2, dtype=torch.int32, device=dev), final_T=torch.zeros(H * W, device=dev),
         n_contrib=torch.zeros(H * W, dtype=torch.int32, device=dev))
     p = _dgm_lib.ptr
-    rc = lib.dgr_export_state(P, W, H, R_cap, p(geom), p(binning), p(img), p(o["depths"]), p(o["means2D"]),
+    rc = lib.dgr_export_state(P, W, H, R_cap, ws.geom, ws.binning, ws.img, p(o["depths"]), p(o["means2D"]),
                               p(o["cov3D"]), p(o["conic_opacity"]), p(o["rgb"]), p(o["tiles_touched"]),
                               p(o["clamped"]), p(o["point_list_keys"]), p(o["point_list"]), p(o["ranges"]),
                               p(o["final_T"]), p(o["n_contrib"]), _dgm_lib.stream_ptr())

@@ -142,6 +142,7 @@ int dgr_export_state(int P, int W, int H, int64_t R_cap,
 #define DGM_K_RENDER_FWD 4
 #define DGM_K_RENDER_BWD 5
 #define DGM_K_PREPROCESS_BWD 6
+#define DGM_K_COUNT_TILES 7
 #define DGM_K_COUNT 16
 int dgm_profile_enable(int on);
 int dgm_profile_read(float* ms_host, int n);

@@ -52,14 +52,11 @@ def run_ours(sc, cam, bg, degree=3, use_colors=False, use_cov=False, dpix=None, 
     color, radii = dgr.GaussianRasterizer(rs)(**kw)
     out = dict(color=color.detach(), radii=radii)
     fn = color.grad_fn
-    saved = fn.saved_tensors
-    _, _, geom, binning, img, status = saved
-    st = status.cpu()
+    st = fn.ws.status_tensor().cpu()
     R = int(st[0])
     assert int(st[1]) == 0
     out["R"] = R
-    out.update(dgr.export_state(leaves["means3D"].shape[0], cam.image_width, cam.image_height, fn.R_cap, geom,
-                                binning, img, R))
+    out.update(dgr.export_state(leaves["means3D"].shape[0], cam.image_width, cam.image_height, fn.ws, R))
     if dpix is not None:
         color.backward(dpix)
         out["grads"] = {k: (v.grad.detach() if v.grad is not None else None) for k, v in leaves.items()}
@@ -102,7 +99,7 @@ def run_ref(sc, cam, bg, degree=3, use_colors=False, use_cov=False, dpix=None, s
     return out
 
 
-def compare(ours, ref, vis_only_fields=True, tol=TOL, check_grads=True, label=""):
+def compare(ours, ref, tol=TOL, check_grads=True, label="", skip=()):
     vis = ref["radii"] > 0
     # ---- integer / bit-exact state
     assert torch.equal(ours["radii"], ref["radii"]), f"{label} radii"
@@ -117,7 +114,7 @@ def compare(ours, ref, vis_only_fields=True, tol=TOL, check_grads=True, label=""
     assert torch.equal(ours["n_contrib"], ref["n_contrib"]), f"{label} n_contrib"
     # ---- fp32 state within tolerance
     for k in ("cov3D", "conic_opacity", "rgb"):
-        if k in ref and ref[k].numel():
+        if k in ref and ref[k].numel() and k not in skip:
             assert util.rel_err(ours[k][vis], ref[k][vis]) < tol, f"{label} {k}"
     assert util.rel_err(ours["final_T"], ref["final_T"]) < tol, f"{label} final_T"
     assert util.rel_err(ours["color"], ref["color"]) < tol, f"{label} color"
@@ -151,12 +148,14 @@ def test_bit_exact_against_reference(n, W, H, degree, colors, cov, scale):
     dpix = torch.randn(3, H, W, generator=torch.Generator().manual_seed(1)).cuda()
     a = run_ours(sc, cam, bg, degree, colors, cov, dpix)
     b = run_ref(sc, cam, bg, degree, colors, cov, dpix)
-    compare(a, b, label=f"n={n} {W}x{H} deg={degree}")
+    # with precomputed inputs the reference leaves those state arrays unwritten
+    skip = (("cov3D",) if cov else ()) + (("rgb",) if colors else ())
+    compare(a, b, label=f"n={n} {W}x{H} deg={degree}", skip=skip)
 
 
 @needs_ref
 def test_long_tile_list_global_sort_path():
-    """More instances in one tile than the shared-memory sort holds (6144)."""
+    """More instances in one tile than the shared-memory sort holds (6016)."""
     n = 9000
     sc, cam = util.small_scene(n=n, W=64, H=64, seed=2, scale=0.02)
     sc["means3D"] = sc["means3D"] * 0.02  # everything lands on the centre tiles
@@ -165,7 +164,7 @@ def test_long_tile_list_global_sort_path():
     bg = torch.zeros(3, device="cuda")
     dpix = torch.randn(3, 64, 64, generator=torch.Generator().manual_seed(3)).cuda()
     a, b = run_ours(sc, cam, bg, 3, False, False, dpix), run_ref(sc, cam, bg, 3, False, False, dpix)
-    assert int((b["ranges"][:, 1] - b["ranges"][:, 0]).max()) > 6144
+    assert int((b["ranges"][:, 1] - b["ranges"][:, 0]).max()) > 6016
     compare(a, b, label="long list")
 
 
@@ -225,8 +224,14 @@ def test_edge_cases_empty_and_culled():
           rotations=sc["rotations"])
     with pytest.raises(Exception, match="scale/rotation pair"):
         r(means3D=sc["means3D"], means2D=None, opacities=sc["opacities"], shs=sc["shs"])
-    vis = r.markVisible(sc["means3D"])
-    assert vis.dtype == torch.bool and not bool(vis.any())
+    vis = r.markVisible(sc["means3D"])       # near-plane test only (auxiliary.h:154)
+    ones = torch.ones(sc["means3D"].shape[0], 1, device="cuda")
+    pz = (torch.cat([sc["means3D"], ones], 1) @ cam.world_view_transform)[:, 2]
+    assert vis.dtype == torch.bool and torch.equal(vis, pz > 0.2)
+    ref = util.load_reference_rasterizer()
+    if ref is not None:
+        rs_ref = synth.raster_settings_for(cam, bg, settings_cls=ref.GaussianRasterizationSettings)
+        assert torch.equal(vis, ref.GaussianRasterizer(rs_ref).markVisible(sc["means3D"]))
 
 
 def test_workspace_overflow_is_reported_not_silent():
@@ -238,13 +243,13 @@ def test_workspace_overflow_is_reported_not_silent():
     args = (bg, sc["means3D"], None, sc["opacities"], sc["scales"], sc["rotations"], 1.0, None,
             cam.world_view_transform, cam.full_proj_transform, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2),
             cam.image_height, cam.image_width, sc["shs"], 3, cam.camera_center, False)
-    color, radii, geom, binning, img, status = dgr._raw_forward(*args, 32)
-    st = status.cpu()
+    color, radii, ws = dgr._raw_forward(*args, 32)
+    st = ws.status_tensor().cpu()
     assert int(st[1]) == 1 and int(st[0]) > 32
     assert torch.allclose(color[2], torch.full_like(color[2], 0.3))
     cap = dgr._round_cap(int(st[0]))
-    color2, *_, status2 = dgr._raw_forward(*args, cap)
-    assert int(status2.cpu()[1]) == 0 and float((color2 - color).abs().max()) > 0.05
+    color2, _, ws2 = dgr._raw_forward(*args, cap)
+    assert int(ws2.status_tensor().cpu()[1]) == 0 and float((color2 - color).abs().max()) > 0.05
 
 
 def test_full_size_properties():

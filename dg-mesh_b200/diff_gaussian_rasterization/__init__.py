@@ -241,7 +241,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         base = flat.data_ptr()
         ptrs = [base + 4 * x for x in offs]
 
-        def view(i, *shape):
+        def gview(i, *shape):
             n = 1
             for d in shape:
                 n *= d
@@ -256,10 +256,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                               ptrs[8] if M else None, ptrs[6], ptrs[7], _dgm_lib.stream_ptr())
         _dgm_lib.check(rc, "dgr_backward")
         # same ordering as the reference (:143-153)
-        return (view(4, P, 3), view(0, P, 3) if ctx.has_m2d else None, view(8, P, M, 3) if sh is not None else None,
-                view(3, P, 3) if col is not None else None, view(2, P, 1),
-                view(6, P, 3) if sc is not None else None, view(7, P, 4) if rot is not None else None,
-                view(5, P, 6) if cov is not None else None, None)
+        return (gview(4, P, 3), gview(0, P, 3) if ctx.has_m2d else None,
+                gview(8, P, M, 3) if sh is not None else None, gview(3, P, 3) if col is not None else None,
+                gview(2, P, 1), gview(6, P, 3) if sc is not None else None,
+                gview(7, P, 4) if rot is not None else None, gview(5, P, 6) if cov is not None else None, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):

@@ -1,0 +1,116 @@
+"""Host-side logic of the drop-in `diff_gaussian_rasterization` exercised WITHOUT a GPU: the C
+library is replaced by a recording stub (same symbol table, argument counts checked against the
+ctypes signatures), tensors live on the CPU.  Catches glue errors (argument order, shapes of the
+returned gradients, capacity policy) before a GPU run."""
+import math
+
+import pytest
+import torch
+
+import _dgm_lib
+import diff_gaussian_rasterization as dgr
+import synth
+
+
+class StubLib:
+    def __init__(self):
+        self.calls = []
+        self.R = 1000
+
+    def __getattr__(self, name):
+        if name not in _dgm_lib.SIGNATURES:
+            raise AttributeError(name)
+        nargs = len(_dgm_lib.SIGNATURES[name][1])
+
+        def fn(*a):
+            assert len(a) == nargs, f"{name}: {len(a)} args, header declares {nargs}"
+            self.calls.append((name, a))
+            if name == "dgr_workspace_sizes":
+                a[4]._obj.value, a[5]._obj.value, a[6]._obj.value = 4096, 60 * a[3] + 128, 8192
+            return 0
+        return fn
+
+
+@pytest.fixture()
+def stub(monkeypatch):
+    st = StubLib()
+    monkeypatch.setattr(_dgm_lib, "lib", lambda: st)
+    monkeypatch.setattr(_dgm_lib, "stream_ptr", lambda: 0)
+    monkeypatch.setattr(dgr, "_f32c", lambda t, name: None if (t is None or t.numel() == 0) else t.contiguous())
+    # status read-back: pretend R instances, no overflow
+    monkeypatch.setattr(dgr._Workspace, "status_tensor",
+                        lambda self: torch.tensor([st.R, 0, 0, 0, 0, 0, 0, 0], dtype=torch.int32))
+    monkeypatch.setattr(dgr._Sizing, "watch", classmethod(lambda cls, status, key, cap: None))
+    dgr._Sizing.hint.clear()
+    dgr._ws_sizes.clear()
+    yield st
+
+
+def _byref_shim(monkeypatch):
+    # ctypes passes c_size_t by reference; the stub reads `_obj`
+    pass
+
+
+def test_forward_backward_glue(stub, monkeypatch):
+    import ctypes
+    # emulate ctypes by-reference semantics for the size query
+    orig = dgr._sizes
+
+    def sizes(P, W, H, R_cap):
+        return (4096, 60 * R_cap + 128, 8192, 4096, (60 * R_cap + 128 + 511) // 512 * 512, 8192)
+    monkeypatch.setattr(dgr, "_sizes", sizes)
+    sc = synth.gaussian_scene(n=64, seed=0)
+    cam = synth.look_at_camera(width=48, height=32)
+    rs = synth.raster_settings_for(cam, torch.ones(3), settings_cls=dgr.GaussianRasterizationSettings)
+    leaves = {k: sc[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    color, radii = dgr.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                              shs=leaves["shs"], scales=leaves["scales"],
+                                              rotations=leaves["rotations"])
+    assert color.shape == (3, 32, 48) and radii.shape == (64,) and radii.dtype == torch.int32
+    color.backward(torch.ones_like(color))
+    names = [c[0] for c in stub.calls]
+    assert names.count("dgr_forward") == 1 and names.count("dgr_backward") == 1
+    for k, shape in dict(means3D=(64, 3), opacities=(64, 1), scales=(64, 3), rotations=(64, 4), shs=(64, 16, 3)).items():
+        assert leaves[k].grad is not None and tuple(leaves[k].grad.shape) == shape, k
+    assert tuple(m2d.grad.shape) == (64, 3)
+    # every gradient sub-buffer handed to the library is 16-byte aligned
+    bwd = [c for c in stub.calls if c[0] == "dgr_backward"][0][1]
+    for ptr in bwd[24:33]:
+        assert ptr is None or ptr % 16 == 0
+    # second call for the same shape reuses the capacity hint (no sizing sync path)
+    n_before = len(stub.calls)
+    dgr.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                               shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+    assert [c[0] for c in stub.calls[n_before:]].count("dgr_forward") == 1
+    cap = [c for c in stub.calls if c[0] == "dgr_forward"][-1][1][26]
+    assert cap == dgr._grow(stub.R) and cap % 32 == 0
+
+
+def test_precomputed_inputs_and_errors(stub, monkeypatch):
+    monkeypatch.setattr(dgr, "_sizes", lambda P, W, H, R: (4096, 60 * R + 128, 8192, 4096,
+                                                           (60 * R + 128 + 511) // 512 * 512, 8192))
+    sc = synth.gaussian_scene(n=32, seed=1)
+    cam = synth.look_at_camera(width=32, height=32)
+    rs = synth.raster_settings_for(cam, torch.zeros(3), settings_cls=dgr.GaussianRasterizationSettings)
+    r = dgr.GaussianRasterizer(rs)
+    cols = torch.rand(32, 3, requires_grad=True)
+    cov = torch.rand(32, 6, requires_grad=True)
+    m3 = sc["means3D"].clone().requires_grad_(True)
+    color, _ = r(means3D=m3, means2D=None, opacities=sc["opacities"], colors_precomp=cols, cov3D_precomp=cov)
+    color.sum().backward()
+    assert tuple(cols.grad.shape) == (32, 3) and tuple(cov.grad.shape) == (32, 6) and tuple(m3.grad.shape) == (32, 3)
+    fwd = [c for c in stub.calls if c[0] == "dgr_forward"][0][1]
+    assert fwd[7] is None and fwd[8] is not None          # shs absent, colors_precomp present
+    assert fwd[10] is None and fwd[12] is None and fwd[13] is not None
+    with pytest.raises(Exception, match="excatly one of either SHs"):
+        r(means3D=m3, means2D=None, opacities=sc["opacities"], scales=sc["scales"], rotations=sc["rotations"])
+    with pytest.raises(Exception, match="scale/rotation pair"):
+        r(means3D=m3, means2D=None, opacities=sc["opacities"], shs=sc["shs"], scales=sc["scales"])
+
+
+def test_settings_fields_match_reference_order():
+    assert dgr.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+    assert math.isclose(dgr._cap_from_bytes(60 * 4096 + 128), 4096)

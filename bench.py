@@ -127,37 +127,67 @@ def run_frames(dgr, synth, leaves, cams, dpix, bg, frame_ids, staged=None):
 
 
 class HostFeed:
-    """e2e leg: every step, each frame's camera (35 floats) and pixel gradient (3xHxW fp32, standing in
-    for the ground-truth image a training step uploads) are copied from PINNED HOST memory on a side
-    stream, overlapped with the rendering of the previous frames; the step's result (a checksum of the
-    accumulated gradient) is read back to the host."""
+    """e2e leg: every step the frames' cameras (35 floats each) and pixel gradients (3xHxW fp32, standing
+    in for the ground-truth images a training step uploads) are copied from PINNED HOST memory on a side
+    stream, overlapped with rendering; the step's result (a checksum of the accumulated gradient) is
+    read back to the host."""
 
     def __init__(self, cams, dpix, frames, dev):
         self.frames = frames
-        self.h = {k: (cams[k].world_view_transform.cpu().pin_memory(), cams[k].full_proj_transform.cpu().pin_memory(),
-                      cams[k].camera_center.cpu().pin_memory(), dpix[k].cpu().pin_memory()) for k in frames}
-        self.d = {k: tuple(torch.empty_like(t, device=dev) for t in self.h[k]) for k in frames}
-        self.ev = {k: torch.cuda.Event() for k in frames}
+        F = len(frames)
+        self.h_cam = torch.stack([torch.cat([cams[k].world_view_transform.cpu().reshape(-1),
+                                             cams[k].full_proj_transform.cpu().reshape(-1),
+                                             cams[k].camera_center.cpu().reshape(-1)]) for k in frames]).pin_memory()
+        self.h_dpix = torch.stack([dpix[k].cpu() for k in frames]).pin_memory()
+        self.d_cam = torch.empty_like(self.h_cam, device=dev)
+        self.d_dpix = torch.empty_like(self.h_dpix, device=dev)
+        self.views = [self.d_cam[i, 0:16].view(4, 4) for i in range(F)]
+        self.projs = [self.d_cam[i, 16:32].view(4, 4) for i in range(F)]
+        self.campos = [self.d_cam[i, 32:35] for i in range(F)]
+        self.ev_cam, self.ev_dpix, self.consumed = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.consumed = torch.cuda.Event()
         self.consumed.record()
         self.out_host = torch.zeros(1).pin_memory()
-        self.h2d_bytes = sum(sum(t.numel() * 4 for t in self.h[k]) for k in frames)
+        self.h2d_bytes = (self.h_cam.numel() + self.h_dpix.numel()) * 4
 
     def upload(self):
         self.copy_stream.wait_event(self.consumed)  # the previous step no longer reads the staging buffers
         with torch.cuda.stream(self.copy_stream):
-            for k in self.frames:
-                for src, dst in zip(self.h[k], self.d[k]):
-                    dst.copy_(src, non_blocking=True)
-                self.ev[k].record(self.copy_stream)
-        return {k: (self.ev[k],) + self.d[k] for k in self.frames}
+            self.d_cam.copy_(self.h_cam, non_blocking=True)
+            self.ev_cam.record(self.copy_stream)
+            self.d_dpix.copy_(self.h_dpix, non_blocking=True)
+            self.ev_dpix.record(self.copy_stream)
 
     def finish(self, result):
         self.consumed.record()
         self.out_host.copy_(result.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the host now holds the step's result
         return float(self.out_host[0])
+
+
+def batch_settings(dgr, cams, bg, frames, views=None, projs=None, campos=None):
+    out = []
+    for i, k in enumerate(frames):
+        c = cams[k]
+        out.append(dgr.GaussianRasterizationSettings(
+            image_height=HEIGHT, image_width=WIDTH, tanfovx=math.tan(c.FoVx * 0.5), tanfovy=math.tan(c.FoVy * 0.5),
+            bg=bg, scale_modifier=1.0, viewmatrix=views[i] if views else c.world_view_transform,
+            projmatrix=projs[i] if projs else c.full_proj_transform, sh_degree=3,
+            campos=campos[i] if campos else c.camera_center, prefiltered=False, debug=False))
+    return out
+
+
+def run_batch(dgr, leaves, settings, dpix_stacked, wait_fwd=None, wait_bwd=None):
+    """forward + backward of a frame batch through BatchGaussianRasterizer (this repo's batched API)."""
+    if wait_fwd is not None:
+        torch.cuda.current_stream().wait_event(wait_fwd)
+    color, radii = dgr.BatchGaussianRasterizer(settings)(
+        means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"], shs=leaves["shs"],
+        scales=leaves["scales"], rotations=leaves["rotations"])
+    if wait_bwd is not None:
+        torch.cuda.current_stream().wait_event(wait_bwd)
+    color.backward(dpix_stacked)
+    return color
 
 
 def timed(fn, steps, warmup, world):
@@ -240,9 +270,17 @@ def main():
     bg = torch.ones(3, device=dev)
     my_frames = [k for k in range(FRAMES) if k % world == rank]
 
+    ours = a.impl == "ours"
+    if ours:
+        dev_settings = batch_settings(dgr, cams, bg, my_frames)
+        dpix_stacked = torch.stack([dpix[k] for k in my_frames]).contiguous()
+
     def step():
         gflat.zero_()
-        run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames)
+        if ours:
+            run_batch(dgr, leaves, dev_settings, dpix_stacked)
+        else:
+            run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames)
         if world > 1:
             dist.all_reduce(gflat)  # the one collective of the step
 
@@ -255,11 +293,19 @@ def main():
 
     # ---- e2e leg: host buffers, copies inside the timed region
     feed = HostFeed(cams, dpix, my_frames, dev)
+    if ours:
+        feed_settings = batch_settings(dgr, cams, bg, my_frames, feed.views, feed.projs, feed.campos)
 
     def step_e2e():
-        staged = feed.upload()
+        feed.upload()
         gflat.zero_()
-        run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged)
+        if ours:
+            run_batch(dgr, leaves, feed_settings, feed.d_dpix, wait_fwd=feed.ev_cam, wait_bwd=feed.ev_dpix)
+        else:
+            torch.cuda.current_stream().wait_event(feed.ev_dpix)
+            staged = {k: (feed.ev_dpix, feed.views[i], feed.projs[i], feed.campos[i], feed.d_dpix[i])
+                      for i, k in enumerate(my_frames)}
+            run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged)
         if world > 1:
             dist.all_reduce(gflat)
         feed.finish(gflat.sum())
@@ -278,6 +324,8 @@ def main():
                                "step = 8-frame batch (8 ring cameras), frames sharded over ranks",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "frames_per_step": FRAMES,
                    "parallelism": f"dp{world} over frames" + (", 1 NCCL all-reduce of grads" if world > 1 else ""),
+                   "api": "BatchGaussianRasterizer (frame batch, in-kernel gradient accumulation)" if ours
+                          else "GaussianRasterizer per frame (reference API)",
                    "l2_policy": "per-step working set (8 frames x ~90 MB instance records + 24 MB parameters "
                                 "+ 62 MB pixel gradients) exceeds the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -339,7 +387,7 @@ def main():
                                    "40 B instance record), not HBM-bound: see DESIGN.md 'roofline'"}
         out["kernel_ms"] = kern_ms
         out["num_rendered_mean"] = R_mean
-        out["gpu_launches"] = 7 * len(my_frames) * a.steps * world
+        out["gpu_launches"] = 8 * len(my_frames) * a.steps * world
         if rank == 0 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_port()
     if rank == 0:

@@ -24,6 +24,11 @@ SIGNATURES = {
                             c_float, c_float, c_int, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P]),
     "dgr_backward": (c_int, [c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P,
                              c_float, c_float, P, P, P, c_int64, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "dgr_forward_batch": (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_float, P, P, P, P, P,
+                                  P, P, c_int, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, c_int, P]),
+    "dgr_backward_batch": (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P,
+                                   P, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P, P, P, P, P, P, P,
+                                   P, c_int, P]),
     "dgr_mark_visible": (c_int, [c_int, P, P, P, P, P]),
     "dgr_export_state": (c_int, [c_int, c_int, c_int, c_int64, P, P, P] + [P] * 12 + [P]),
     "dgm_profile_enable": (c_int, [c_int]),

@@ -134,7 +134,7 @@ int dgr_backward(int P, int D, int M, const float* background, int W, int H, con
   if (P < 0 || W <= 0 || H <= 0 || R_cap < 0) return bad("dgr_backward: negative size");
   if (P == 0) return DGM_OK;
   if (!background || !means3D || !viewmatrix || !projmatrix || !cam_pos || !geom_ws || !binning_ws || !img_ws ||
-      !dL_dpix || !dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale ||
+      !dL_dpix || !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale ||
       !dL_drot)
     return bad("dgr_backward: null required pointer");
   if (shs && !dL_dsh) return bad("dgr_backward: dL_dsh missing");
@@ -147,8 +147,128 @@ int dgr_backward(int P, int D, int M, const float* background, int W, int H, con
   a.geom_ws = geom_ws; a.binning_ws = binning_ws; a.img_ws = img_ws; a.R_cap = R_cap;
   a.dL_dpix = dL_dpix; a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity;
   a.dL_dcolor = dL_dcolor; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh;
-  a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+  a.dL_dscale = dL_dscale; a.dL_drot = dL_drot; a.accumulate = 0;
   return check(dgm::launch_backward(a, (cudaStream_t)stream));
+}
+
+namespace {
+// internal side streams + fork/join events for the frame batches (created once per process)
+struct BatchStreams {
+  cudaStream_t s[4] = {};
+  cudaEvent_t fork = nullptr, join[4] = {}, chain[2] = {};
+  bool ok = false;
+  bool init() {
+    if (ok) return true;
+    for (int i = 0; i < 4; ++i) {
+      if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
+    for (int i = 0; i < 2; ++i)
+      if (cudaEventCreateWithFlags(&chain[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    ok = true;
+    return true;
+  }
+};
+BatchStreams g_bs;
+}  // namespace
+
+int dgr_forward_batch(int F, int P, int D, int M, const float* background, int W, int H, const float* means3D,
+                      const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+                      float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                      const float* viewmatrices, const float* projmatrices, const float* cam_poses,
+                      const float* tan_fovx_host, const float* tan_fovy_host, int prefiltered, float* out_color,
+                      int* radii, void* geom_ws, size_t geom_stride, void* binning_ws, size_t binning_stride,
+                      int64_t R_cap, void* img_ws, size_t img_stride, int32_t* status, int n_streams, void* stream) {
+  if (F <= 0 || !tan_fovx_host || !tan_fovy_host || !viewmatrices || !projmatrices || !cam_poses)
+    return bad("dgr_forward_batch: bad argument");
+  size_t gb, bb, ib;
+  if (dgr_workspace_sizes(P, W, H, R_cap, &gb, &bb, &ib) != DGM_OK) return DGM_E_BADARG;
+  if (geom_stride < gb || binning_stride < bb || img_stride < ib || (geom_stride | binning_stride | img_stride) & 127) {
+    strncpy(g_last_error, "dgr_forward_batch: workspace stride too small / unaligned", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  const int NS = n_streams < 1 ? 1 : (n_streams > 4 ? 4 : n_streams);
+  cudaStream_t main_s = (cudaStream_t)stream;
+  const bool multi = NS > 1 && F > 1 && P > 0;
+  if (multi) {
+    if (!g_bs.init()) return check(cudaGetLastError());
+    cudaEventRecord(g_bs.fork, main_s);
+    for (int i = 0; i < NS; ++i) cudaStreamWaitEvent(g_bs.s[i], g_bs.fork, 0);
+  }
+  int rc = DGM_OK;
+  for (int f = 0; f < F && rc == DGM_OK; ++f) {
+    cudaStream_t s = multi ? g_bs.s[f % NS] : main_s;
+    rc = dgr_forward(P, D, M, background, W, H, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
+                     rotations, cov3D_precomp, viewmatrices + 16 * f, projmatrices + 16 * f, cam_poses + 3 * f,
+                     tan_fovx_host[f], tan_fovy_host[f], prefiltered, out_color + (size_t)f * 3 * W * H,
+                     radii ? radii + (size_t)f * P : nullptr, (char*)geom_ws + f * geom_stride, geom_stride,
+                     (char*)binning_ws + f * binning_stride, binning_stride, R_cap, (char*)img_ws + f * img_stride,
+                     img_stride, status + f * DGR_STATUS_WORDS, s);
+  }
+  if (multi) {
+    for (int i = 0; i < NS; ++i) {
+      cudaEventRecord(g_bs.join[i], g_bs.s[i]);
+      cudaStreamWaitEvent(main_s, g_bs.join[i], 0);
+    }
+  }
+  return rc != DGM_OK ? rc : check(cudaGetLastError());
+}
+
+int dgr_backward_batch(int F, int P, int D, int M, const float* background, int W, int H, const float* means3D,
+                       const float* shs, const float* colors_precomp, const float* scales, float scale_modifier,
+                       const float* rotations, const float* cov3D_precomp, const float* viewmatrices,
+                       const float* projmatrices, const float* cam_poses, const float* tan_fovx_host,
+                       const float* tan_fovy_host, const int* radii, void* geom_ws, size_t geom_stride,
+                       void* binning_ws, size_t binning_stride, int64_t R_cap, void* img_ws, size_t img_stride,
+                       const float* dL_dpix, float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
+                       float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                       int n_streams, void* stream) {
+  if (F <= 0 || P < 0 || W <= 0 || H <= 0 || R_cap < 0) return bad("dgr_backward_batch: bad size");
+  if (P == 0) return DGM_OK;
+  if (!background || !means3D || !viewmatrices || !projmatrices || !cam_poses || !tan_fovx_host || !tan_fovy_host ||
+      !geom_ws || !binning_ws || !img_ws || !dL_dpix || !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D ||
+      !dL_dcov3D || !dL_dscale || !dL_drot || (shs && !dL_dsh))
+    return bad("dgr_backward_batch: null required pointer");
+  // two streams suffice: render_bwd(f+1) overlaps preprocess_bwd(f); the preprocess_bwd kernels are
+  // chained by events because they accumulate into the same gradient buffers
+  const bool multi = n_streams > 1 && F > 1;
+  cudaStream_t main_s = (cudaStream_t)stream;
+  if (multi) {
+    if (!g_bs.init()) return check(cudaGetLastError());
+    cudaEventRecord(g_bs.fork, main_s);
+    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(g_bs.s[i], g_bs.fork, 0);
+  }
+  const unsigned gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  (void)gx; (void)gy;
+  cudaError_t e = cudaSuccess;
+  for (int f = 0; f < F && e == cudaSuccess; ++f) {
+    cudaStream_t s = multi ? g_bs.s[f & 1] : main_s;
+    dgm::BwdArgs a;
+    a.P = P; a.D = D; a.M = M; a.background = background; a.W = W; a.H = H;
+    a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales;
+    a.scale_modifier = scale_modifier; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+    a.viewmatrix = viewmatrices + 16 * f; a.projmatrix = projmatrices + 16 * f; a.cam_pos = cam_poses + 3 * f;
+    a.tan_fovx = tan_fovx_host[f]; a.tan_fovy = tan_fovy_host[f];
+    a.radii = radii ? radii + (size_t)f * P : nullptr;
+    a.geom_ws = (char*)geom_ws + f * geom_stride; a.binning_ws = (char*)binning_ws + f * binning_stride;
+    a.img_ws = (char*)img_ws + f * img_stride; a.R_cap = R_cap;
+    a.dL_dpix = dL_dpix + (size_t)f * 3 * W * H;
+    a.dL_dmean2D = dL_dmean2D + (size_t)f * P * 3; a.dL_dconic = nullptr;
+    a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D;
+    a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+    a.accumulate = f > 0;
+    // the accumulating kernel of frame f must follow that of frame f-1
+    e = dgm::launch_backward_split(a, s, (multi && f > 0) ? g_bs.chain[(f - 1) & 1] : nullptr,
+                                   multi ? g_bs.chain[f & 1] : nullptr);
+  }
+  if (multi) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEventRecord(g_bs.join[i], g_bs.s[i]);
+      cudaStreamWaitEvent(main_s, g_bs.join[i], 0);
+    }
+  }
+  return check(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 int dgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,

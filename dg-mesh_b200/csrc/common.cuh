@@ -85,7 +85,7 @@ struct ImgWS {
 struct BinWS {
   unsigned long long* keys;  // [R] unsorted (depth_bits<<32 | gaussian) inside each tile segment
   uint32_t* point_list;      // [R] sorted gaussian ids (== reference point_list)
-  float4* inst_geo;          // [R]   {mean2D.x, mean2D.y, cull half-extent x, y}
+  float4* inst_geo;          // [R]   {mean2D.x, mean2D.y, 2 ln(255 o) cull level, -}
   float4* inst_attr;         // [2R]  {conic.x, conic.y, conic.z, opacity}, {r, g, b, id bits}
   __host__ __device__ static BinWS from(char* base, size_t R, size_t* bytes = nullptr) {
     char* p = base;

@@ -154,9 +154,8 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(
   bg_dot_dpixel += bg_color[1] * dLp1;
   bg_dot_dpixel += bg_color[2] * dLp2;
 
-  float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
-  float last_alpha = 0.f;
-  float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
+  const float mTb = -T_final * bg_dot_dpixel;  // background term of dL/dalpha, times 1/(1-alpha) per record
+  float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;  // colour composited behind the current record
   // d(pixel coordinate)/d(NDC), backward.cu:457-458 (double literal 0.5)
   const float ddelx_dx = 0.5 * W;
   const float ddely_dy = 0.5 * H;
@@ -181,15 +180,16 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(
       const int r = k * 32 + lane;
       bool kp = false;
       if (r < cnt && (lo + r) < wmax) {
-        const float4 ge = s_geo[st][r];
-        const float ddx = fmaxf(fmaxf(bx0 - ge.x, ge.x - bx1), 0.0f);
-        const float ddy = fmaxf(fmaxf(by0 - ge.y, ge.y - by1), 0.0f);
-        kp = !(ddx > ge.z || ddy > ge.w);
+        kp = cull_keep(s_geo[st][r], s_attr[st][2 * r], bx0, bx1, by0, by1);
       }
       keep[k] = __ballot_sync(0xffffffffu, kp);
     }
     // ---- back to front, two records per iteration (packed fp32x2 quadratic form, one
     // butterfly reduction for both).  A is the record nearer the back (processed first).
+    // Per lane only MOMENTS of w = G * dL/dG are accumulated (w, w dx, w dy, w dx^2, w dx dy,
+    // w dy^2) plus the colour weights; the per-Gaussian factors (conic, opacity, viewport
+    // scale) are applied once per (tile, Gaussian) at flush time.  Branch-free: inactive
+    // lanes are masked with selects.
 #pragma unroll
     for (int k = RB / 32 - 1; k >= 0; --k) {
       unsigned mask = keep[k];
@@ -211,56 +211,53 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(
         float2 m3 = __fmul2_rn(dx2, make_float2(coA.y, coB.y));
         m3 = __fmul2_rn(dy2, m3);
         const float2 npow = __ffma2_rn(sq, make_float2(0.5f, 0.5f), m3);  // = -power
-        float v[2][9];
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int i = 0; i < 9; ++i) v[q][i] = 0.f;
+        // order-dependent part (scalar): transmittance and the colour behind each record
+        float wq[2], atq[2];
         bool contrib = false;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const float np = q ? npow.y : npow.x;
-          const float4 con_o = q ? coB : coA;
-          const float dx = q ? dx2.y : dx2.x, dy = q ? dy2.y : dy2.x;
+          const float opac = q ? coB.w : coA.w;
           const int j = q ? jB : jA;
-          // reference: contributor (0-based position) must be < last_contributor
-          if ((q == 0 || two) && (lo + j) < last_contributor && !(np < 0.0f)) {
-            const float G = expf(-np);
-            const float alpha = fminf(0.99f, con_o.w * G);
-            if (!(alpha < 1.0f / 255.0f)) {
-              contrib = true;
-              const float4 col = s_attr[st][2 * j + 1];
-              T = T / (1.f - alpha);
-              const float dchannel_dcolor = alpha * T;
-              float dL_dalpha = 0.0f;
-              accum0 = last_alpha * lc0 + (1.f - last_alpha) * accum0;
-              lc0 = col.x;
-              dL_dalpha += (col.x - accum0) * dLp0;
-              v[q][6] = dchannel_dcolor * dLp0;
-              accum1 = last_alpha * lc1 + (1.f - last_alpha) * accum1;
-              lc1 = col.y;
-              dL_dalpha += (col.y - accum1) * dLp1;
-              v[q][7] = dchannel_dcolor * dLp1;
-              accum2 = last_alpha * lc2 + (1.f - last_alpha) * accum2;
-              lc2 = col.z;
-              dL_dalpha += (col.z - accum2) * dLp2;
-              v[q][8] = dchannel_dcolor * dLp2;
-              dL_dalpha *= T;
-              last_alpha = alpha;
-              dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-              const float dL_dG = con_o.w * dL_dalpha;
-              const float gdx = G * dx;
-              const float gdy = G * dy;
-              const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-              const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-              v[q][0] = dL_dG * dG_ddelx * ddelx_dx;
-              v[q][1] = dL_dG * dG_ddely * ddely_dy;
-              v[q][2] = -0.5f * gdx * dx * dL_dG;
-              v[q][3] = -0.5f * gdx * dy * dL_dG;
-              v[q][4] = -0.5f * gdy * dy * dL_dG;
-              v[q][5] = G * dL_dalpha;
-            }
-          }
+          const float4 col = s_attr[st][2 * j + 1];
+          // reference: contributor (0-based position) < last_contributor, power <= 0, alpha >= 1/255
+          const bool pre = (q == 0 || two) && (lo + j) < last_contributor && !(np < 0.0f);
+          const float G = expf(-np);
+          const float alpha = fminf(0.99f, opac * G);
+          const bool act = pre && !(alpha < 1.0f / 255.0f);
+          contrib |= act;
+          const float r = __fdividef(1.0f, 1.0f - alpha);
+          const float a_eff = act ? alpha : 0.0f;  // inactive lanes leave every state variable unchanged
+          T *= act ? r : 1.0f;
+          const float d0 = col.x - accum0, d1 = col.y - accum1, d2 = col.z - accum2;
+          float dLa = d0 * dLp0;
+          dLa = fmaf(d1, dLp1, dLa);
+          dLa = fmaf(d2, dLp2, dLa);
+          dLa = fmaf(dLa, T, mTb * r);
+          wq[q] = act ? (G * opac) * dLa : 0.0f;
+          atq[q] = a_eff * T;
+          // colour behind the NEXT record: alpha c + (1 - alpha) accum  (backward.cu:507, evaluated eagerly)
+          accum0 = fmaf(a_eff, d0, accum0);
+          accum1 = fmaf(a_eff, d1, accum1);
+          accum2 = fmaf(a_eff, d2, accum2);
+        }
+        // moments of w for both records at once (packed)
+        float v[2][9];
+        {
+          const float2 w2 = make_float2(wq[0], wq[1]), at2 = make_float2(atq[0], atq[1]);
+          const float2 wx = __fmul2_rn(w2, dx2), wy = __fmul2_rn(w2, dy2);
+          const float2 wxx = __fmul2_rn(wx, dx2), wxy = __fmul2_rn(wx, dy2), wyy = __fmul2_rn(wy, dy2);
+          const float2 c0 = __fmul2_rn(at2, make_float2(dLp0, dLp0)), c1 = __fmul2_rn(at2, make_float2(dLp1, dLp1)),
+                       c2 = __fmul2_rn(at2, make_float2(dLp2, dLp2));
+          v[0][0] = w2.x, v[1][0] = w2.y;
+          v[0][1] = wx.x, v[1][1] = wx.y;
+          v[0][2] = wy.x, v[1][2] = wy.y;
+          v[0][3] = wxx.x, v[1][3] = wxx.y;
+          v[0][4] = wxy.x, v[1][4] = wxy.y;
+          v[0][5] = wyy.x, v[1][5] = wyy.y;
+          v[0][6] = c0.x, v[1][6] = c0.y;
+          v[0][7] = c1.x, v[1][7] = c1.y;
+          v[0][8] = c2.x, v[1][8] = c2.y;
         }
         if (__any_sync(0xffffffffu, contrib)) {
           float r8, r9;
@@ -286,10 +283,15 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(
         acc[q] = 0.f;
       }
       if (nz) {
+        // moments -> gradients (backward.cu:531-554): a[0..5] = sums of w, w dx, w dy, w dx^2, w dx dy, w dy^2
+        const float4 con_o = s_attr[st][2 * tid];
         const uint32_t id = __float_as_uint(s_attr[st][2 * tid + 1].w);
+        const float g_mx = -ddelx_dx * (con_o.x * a[1] + con_o.y * a[2]);
+        const float g_my = -ddely_dy * (con_o.z * a[2] + con_o.y * a[1]);
+        const float g_op = (con_o.w != 0.0f) ? a[0] / con_o.w : 0.0f;
         float* dst = reinterpret_cast<float*>(grad_acc + 3 * (size_t)id);
-        red_add_v4(dst, a[0], a[1], a[2], a[3]);
-        red_add_v4(dst + 4, a[4], a[5], a[6], a[7]);
+        red_add_v4(dst, g_mx, g_my, -0.5f * a[3], -0.5f * a[4]);
+        red_add_v4(dst + 4, -0.5f * a[5], g_op, a[6], a[7]);
         atomicAdd(dst + 8, a[8]);
       }
     }
@@ -386,6 +388,9 @@ __device__ __forceinline__ float3 sh_backward(int deg, const float3 pos, const f
   return r;
 }
 
+// write v, or add it to what the buffer holds (never reads the buffer unless accumulating)
+__device__ __forceinline__ void acc_store(float* p, float v, int accumulate) { *p = accumulate ? *p + v : v; }
+
 __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
     int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
     const float* __restrict__ shs, const float* __restrict__ scales, const float* __restrict__ rotations,
@@ -394,7 +399,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
     const float* __restrict__ cam_pos, GeomWS g, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D,
     float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscale,
-    float* __restrict__ dL_drot) {
+    float* __restrict__ dL_drot, int accumulate) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
   const bool visible = radii[idx] > 0;
@@ -411,11 +416,13 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
   dL_dmean2D[3 * idx + 0] = dm2.x;
   dL_dmean2D[3 * idx + 1] = dm2.y;
   dL_dmean2D[3 * idx + 2] = 0.f;
-  reinterpret_cast<float4*>(dL_dconic)[idx] = make_float4(dcon.x, dcon.y, 0.f, dcon.z);
-  dL_dopacity[idx] = dop;
-  dL_dcolor[3 * idx + 0] = dcol.x;
-  dL_dcolor[3 * idx + 1] = dcol.y;
-  dL_dcolor[3 * idx + 2] = dcol.z;
+  if (dL_dconic) reinterpret_cast<float4*>(dL_dconic)[idx] = make_float4(dcon.x, dcon.y, 0.f, dcon.z);
+  // parameter gradients: written, or (frame batches) added to the running sum over frames
+  if (accumulate && !visible) return;  // a culled Gaussian adds nothing
+  acc_store(&dL_dopacity[idx], dop, accumulate);
+  acc_store(&dL_dcolor[3 * idx + 0], dcol.x, accumulate);
+  acc_store(&dL_dcolor[3 * idx + 1], dcol.y, accumulate);
+  acc_store(&dL_dcolor[3 * idx + 2], dcol.z, accumulate);
 
   float dcov[6] = {0, 0, 0, 0, 0, 0};
   float3 dmean = make_float3(0, 0, 0);
@@ -513,12 +520,18 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
       float* dst = dL_dsh + (size_t)idx * M * 3;
       if (M == 16) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i)
-          reinterpret_cast<float4*>(dst)[i] = make_float4(dsh[4 * i], dsh[4 * i + 1], dsh[4 * i + 2], dsh[4 * i + 3]);
+        for (int i = 0; i < 12; ++i) {
+          float4 o = make_float4(dsh[4 * i], dsh[4 * i + 1], dsh[4 * i + 2], dsh[4 * i + 3]);
+          if (accumulate) {
+            const float4 old = reinterpret_cast<float4*>(dst)[i];
+            o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+          }
+          reinterpret_cast<float4*>(dst)[i] = o;
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 48; ++i)
-          if (i < M * 3) dst[i] = dsh[i];
+          if (i < M * 3) acc_store(&dst[i], dsh[i], accumulate);
       }
     }
     // ---------------- 3D covariance -> scale / rotation (backward.cu:279-341)
@@ -575,18 +588,28 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
                2 * y * (dMt.c[1][2] + dMt.c[2][1]) - 4 * z * (dMt.c[1][1] + dMt.c[0][0]);
     }
   }
-  dL_dmean3D[3 * idx + 0] = dmean.x;
-  dL_dmean3D[3 * idx + 1] = dmean.y;
-  dL_dmean3D[3 * idx + 2] = dmean.z;
+  acc_store(&dL_dmean3D[3 * idx + 0], dmean.x, accumulate);
+  acc_store(&dL_dmean3D[3 * idx + 1], dmean.y, accumulate);
+  acc_store(&dL_dmean3D[3 * idx + 2], dmean.z, accumulate);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = dcov[k];
-  dL_dscale[3 * idx + 0] = dscale.x;
-  dL_dscale[3 * idx + 1] = dscale.y;
-  dL_dscale[3 * idx + 2] = dscale.z;
-  reinterpret_cast<float4*>(dL_drot)[idx] = drot;
+  for (int k = 0; k < 6; ++k) acc_store(&dL_dcov3D[6 * idx + k], dcov[k], accumulate);
+  acc_store(&dL_dscale[3 * idx + 0], dscale.x, accumulate);
+  acc_store(&dL_dscale[3 * idx + 1], dscale.y, accumulate);
+  acc_store(&dL_dscale[3 * idx + 2], dscale.z, accumulate);
+  {
+    float4 o = drot;
+    if (accumulate) {
+      const float4 old = reinterpret_cast<float4*>(dL_drot)[idx];
+      o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+    }
+    reinterpret_cast<float4*>(dL_drot)[idx] = o;
+  }
 }
 
-cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s) {
+cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s) { return launch_backward_split(a, s, nullptr, nullptr); }
+
+cudaError_t launch_backward_split(const BwdArgs& a, cudaStream_t s, cudaEvent_t wait_before_pp,
+                                  cudaEvent_t record_after_pp) {
   if (a.P == 0) return cudaSuccess;
   const unsigned gx = (a.W + TILE_X - 1) / TILE_X, gy = (a.H + TILE_Y - 1) / TILE_Y;
   const int T = gx * gy;
@@ -600,12 +623,14 @@ cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s) {
   render_bwd_kernel<<<T, 256, 0, s>>>(im.ranges, im.tile_order, b.inst_geo, b.inst_attr, a.W, a.H, a.background,
                                       im.final_T, im.n_contrib, a.dL_dpix, g.grad_acc);
   g_prof.end(5, s);
+  if (wait_before_pp) cudaStreamWaitEvent(s, wait_before_pp, 0);
   g_prof.begin(6, s);
   preprocess_bwd_kernel<<<(a.P + 127) / 128, 128, 0, s>>>(
       a.P, a.D, a.M, a.means3D, radii, a.shs, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix,
       a.projmatrix, focal_x, focal_y, a.tan_fovx, a.tan_fovy, a.cam_pos, g, a.dL_dmean2D, a.dL_dconic, a.dL_dopacity,
-      a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D, a.dL_dsh, a.dL_dscale, a.dL_drot);
+      a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D, a.dL_dsh, a.dL_dscale, a.dL_drot, a.accumulate);
   g_prof.end(6, s);
+  if (record_after_pp) cudaEventRecord(record_after_pp, s);
   return cudaGetLastError();
 }
 

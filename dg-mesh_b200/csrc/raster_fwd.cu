@@ -240,25 +240,36 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(int T, uint32_t* __restr
   {
     const int tx = tid & 31, seg = tid >> 5;
     const int t = blockIdx.x * 32 + tx;
-    const int r0 = seg * (DEPTH_BUCKETS / 8), r1 = r0 + DEPTH_BUCKETS / 8;
-    uint32_t* row = hist + (size_t)(t < T ? t : 0) * DEPTH_BUCKETS;
+    // this thread owns DEPTH_BUCKETS/8 = 32 consecutive buckets (128 B) of tile t
+    uint4* row = reinterpret_cast<uint4*>(hist + (size_t)(t < T ? t : 0) * DEPTH_BUCKETS + seg * (DEPTH_BUCKETS / 8));
+    uint4 v[8];
     uint32_t sum = 0;
     if (t < T) {
-#pragma unroll 8
-      for (int c = r0; c < r1; ++c) sum += row[c];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        v[c] = row[c];
+        sum += v[c].x + v[c].y + v[c].z + v[c].w;
+      }
     }
     s_part[seg][tx] = sum;
     __syncthreads();
     uint32_t run = 0;
     for (int k = 0; k < seg; ++k) run += s_part[k][tx];
     if (t < T) {
-#pragma unroll 8
-      for (int c = r0; c < r1; ++c) {
-        const uint32_t v = row[c];
-        row[c] = run;
-        run += v;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 o;
+        o.x = run;
+        run += v[c].x;
+        o.y = run;
+        run += v[c].y;
+        o.z = run;
+        run += v[c].z;
+        o.w = run;
+        run += v[c].w;
+        row[c] = o;
       }
-      if (seg == 7) tile_total[t] = run;  // the last segment ends with the column total
+      if (seg == 7) tile_total[t] = run;  // the last segment ends with the tile total
     }
   }
   // ---- last CTA done: scan of the column totals
@@ -448,23 +459,17 @@ __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __rest
     const uint32_t id = (uint32_t)(k & 0xffffffffull);
     const float2 xy = g.means2D[id];
     const float4 co = g.conic_opacity[id];
-    // conservative half extents of { alpha >= 1/255 }: power >= -tau, tau = ln(255 o).
-    // Margins (0.02 on tau, 1e-4 relative + 0.01 px) dwarf fp32 rounding of the blend.
-    float hx, hy;
+    // 2*(ln(255 o) + margin): the level of q = -2 power below which alpha >= 1/255 is possible
+    // (see cull_keep); -1 when the opacity alone rules it out, +inf for a degenerate conic
+    float q2tau;
     const float tau = __logf(255.0f * co.w) + 0.02f;
     const float det = co.x * co.z - co.y * co.y;
-    if (!(tau > 0.0f)) {
-      hx = hy = -1.0f;  // opacity < 1/255: can never pass the alpha test
-    } else if (!(det > 0.0f) || !isfinite(det) || !isfinite(tau)) {
-      hx = hy = 3.0e38f;  // degenerate conic: never cull
-    } else {
-      hx = sqrtf(2.0f * tau * co.z / det) * 1.0001f + 0.01f;
-      hy = sqrtf(2.0f * tau * co.x / det) * 1.0001f + 0.01f;
-      if (!isfinite(hx) || !isfinite(hy)) hx = hy = 3.0e38f;
-    }
+    if (!(tau > 0.0f)) q2tau = -1.0f;
+    else if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f) || !isfinite(det) || !isfinite(tau)) q2tau = 3.0e38f;
+    else q2tau = 2.0f * tau;
     const size_t o = (size_t)range.x + i;
     b.point_list[o] = id;
-    b.inst_geo[o] = make_float4(xy.x, xy.y, hx, hy);
+    b.inst_geo[o] = make_float4(xy.x, xy.y, q2tau, 0.0f);
     b.inst_attr[2 * o] = co;
     b.inst_attr[2 * o + 1] = make_float4(colors[3 * id], colors[3 * id + 1], colors[3 * id + 2], __uint_as_float(id));
   }
@@ -547,10 +552,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const uint2* __restrict
       const int r = k * 32 + lane;
       bool kp = false;
       if (r < nb) {
-        const float4 ge = s_geo[st][r];
-        const float ddx = fmaxf(fmaxf(bx0 - ge.x, ge.x - bx1), 0.0f);
-        const float ddy = fmaxf(fmaxf(by0 - ge.y, ge.y - by1), 0.0f);
-        kp = !(ddx > ge.z || ddy > ge.w);
+        kp = cull_keep(s_geo[st][r], s_attr[st][2 * r], bx0, bx1, by0, by1);
       }
       keep[k] = __ballot_sync(0xffffffffu, kp);
     }

@@ -35,6 +35,7 @@ struct BwdArgs {
   int64_t R_cap;
   const float* dL_dpix;
   float *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor, *dL_dmean3D, *dL_dcov3D, *dL_dsh, *dL_dscale, *dL_drot;
+  int accumulate;  // 0: parameter gradients are written; 1: added to what the buffers hold (frame batches)
 };
 
 // event pairs around kernels (see dgm_profile_enable in include/dgmesh_b200.h)
@@ -56,6 +57,8 @@ extern Profiler g_prof;
 
 cudaError_t launch_forward(const FwdArgs& a, cudaStream_t s);
 cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s);
+// same, with an event to wait on before / to record after the (accumulating) per-Gaussian kernel
+cudaError_t launch_backward_split(const BwdArgs& a, cudaStream_t s, cudaEvent_t wait_before_pp, cudaEvent_t record_after_pp);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, uint8_t* present,
                                 cudaStream_t s);
 cudaError_t launch_export_state(int P, int W, int H, int64_t R_cap, const void* geom_ws, const void* binning_ws,

@@ -204,6 +204,30 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 pos, const flo
   return make_float3(res[0], res[1], res[2]);
 }
 
+// Exact test "can this Gaussian reach alpha >= 1/255 on any pixel of the block [bx0,bx1]x[by0,by1]?":
+// minimise q(d) = a dx^2 + 2 b dx dy + c dy^2 (= -2 power) over the box of offsets d = g - p.  The
+// minimiser of a convex quadratic with its centre outside the box lies on an edge facing the centre,
+// so at most two clamped 1-D minimisations are needed.  geo.z holds 2*(ln(255 o) + margin)
+// (negative: never visible; +inf: degenerate conic, never culled); the margin (0.02 on tau) dwarfs
+// the fp32 rounding of the blend, so a culled record is one the reference `continue`s over.
+__device__ __forceinline__ bool cull_keep(const float4 geo, const float4 con_o, float bx0, float bx1, float by0,
+                                          float by1) {
+  const float X0 = geo.x - bx1, X1 = geo.x - bx0, Y0 = geo.y - by1, Y1 = geo.y - by0;
+  const float ex = fminf(fmaxf(0.0f, X0), X1), ey = fminf(fmaxf(0.0f, Y0), Y1);  // box point nearest the centre
+  const float a = con_o.x, b = con_o.y, c = con_o.z;
+  // edge dx = ex: dy* = clamp(-b ex / c);  edge dy = ey: dx* = clamp(-b ey / a)
+  const float dy1 = fminf(fmaxf(__fdividef(-b * ex, c), Y0), Y1);
+  const float dx2 = fminf(fmaxf(__fdividef(-b * ey, a), X0), X1);
+  const float q1 = a * ex * ex + 2.0f * b * ex * dy1 + c * dy1 * dy1;
+  const float q2 = a * dx2 * dx2 + 2.0f * b * dx2 * ey + c * ey * ey;
+  // a facing edge exists only where the box does not straddle the centre on that axis
+  float qmin = 0.0f;
+  if (ex != 0.0f && ey != 0.0f) qmin = fminf(q1, q2);
+  else if (ex != 0.0f) qmin = q1;
+  else if (ey != 0.0f) qmin = q2;
+  return !(qmin > geo.z);
+}
+
 // this Gaussian's SH coefficients -> registers (only the first ncoef*3 values are valid)
 __device__ __forceinline__ void load_sh(const float* __restrict__ shs, size_t idx, int M, int ncoef, float* s) {
   const float* src = shs + idx * (size_t)M * 3;

@@ -55,8 +55,10 @@ class _Sizing:
         if cls.free:
             ev, host = cls.free.pop()
         else:
-            ev, host = torch.cuda.Event(), torch.empty((_ST_WORDS,), dtype=torch.int32, pin_memory=True)
-        host.copy_(status, non_blocking=True)
+            ev, host = torch.cuda.Event(), torch.empty((64 * _ST_WORDS,), dtype=torch.int32, pin_memory=True)
+        n = status.numel()
+        host[:n].copy_(status.reshape(-1), non_blocking=True)
+        host[n:n + 1].fill_(-1) if n < host.numel() else None
         ev.record()
         cls.pending.append((ev, host, key, cap))
 
@@ -71,7 +73,11 @@ class _Sizing:
             if block:
                 ev.synchronize()
             if block or ev.query():
-                R, ovf = int(host[0]), int(host[1])
+                R, ovf = 0, 0
+                for f in range(64):  # one 8-word block per frame, terminated by -1
+                    if int(host[8 * f]) < 0:
+                        break
+                    R, ovf = max(R, int(host[8 * f])), ovf | int(host[8 * f + 1])
                 g = _grow(R)
                 if g > cls.hint.get(key, 0):
                     cls.hint[key] = g
@@ -232,9 +238,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         M = int(sh.shape[1]) if sh is not None else 0
         # all nine gradients in one allocation (each sub-buffer 16-byte aligned for vector stores):
-        # m2d[P,3] conic[P,4] opac[P] col[P,3] m3d[P,3] cov[P,6] scale[P,3] rot[P,4] sh[P,M,3]
+        # m2d[P,3] (conic: not materialised) opac[P] col[P,3] m3d[P,3] cov[P,6] scale[P,3] rot[P,4] sh[P,M,3]
         offs, o = [], 0
-        for w in (3, 4, 1, 3, 3, 6, 3, 4, 3 * M):
+        for w in (3, 0, 1, 3, 3, 6, 3, 4, 3 * M):
             offs.append(o)
             o = (o + P * w + 3) // 4 * 4
         flat = torch.empty((max(o, 1),), dtype=torch.float32, device=means3D.device)
@@ -252,7 +258,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         rc = lib.dgr_backward(P, rs.sh_degree, M, p(bg), W, H, p(means3D), p(sh), p(col), p(sc),
                               float(rs.scale_modifier), p(rot), p(cov), p(view), p(proj), p(campos),
                               float(rs.tanfovx), float(rs.tanfovy), p(radii), ws.geom, ws.binning, ws.R_cap, ws.img,
-                              p(dpix), ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5],
+                              p(dpix), ptrs[0], None, ptrs[2], ptrs[3], ptrs[4], ptrs[5],
                               ptrs[8] if M else None, ptrs[6], ptrs[7], _dgm_lib.stream_ptr())
         _dgm_lib.check(rc, "dgr_backward")
         # same ordering as the reference (:143-153)
@@ -260,6 +266,168 @@ class _RasterizeGaussians(torch.autograd.Function):
                 gview(8, P, M, 3) if sh is not None else None, gview(3, P, 3) if col is not None else None,
                 gview(2, P, 1), gview(6, P, 3) if sc is not None else None,
                 gview(7, P, 4) if rot is not None else None, gview(5, P, 6) if cov is not None else None, None)
+
+
+_N_STREAMS = int(os.environ.get("DGMESH_B200_STREAMS", "2"))
+
+
+class _BatchWorkspace:
+    """F per-frame workspaces + F status blocks in one allocation (see dgr_forward_batch)."""
+    __slots__ = ("buf", "geom", "binning", "img", "status", "gs", "bs", "is_", "R_cap", "F")
+
+    def __init__(self, F, P, W, H, R_cap, dev):
+        _, _, _, ga, ba, ia = _sizes(P, W, H, R_cap)
+        if F > 63:
+            raise ValueError("at most 63 frames per batch")
+        self.buf = torch.empty((F * (ga + ba + ia) + 32 * F,), dtype=torch.uint8, device=dev)
+        base = self.buf.data_ptr()
+        self.geom, self.binning, self.img = base, base + F * ga, base + F * (ga + ba)
+        self.status = base + F * (ga + ba + ia)
+        self.gs, self.bs, self.is_, self.R_cap, self.F = ga, ba, ia, R_cap, F
+
+    def status_tensor(self):
+        return self.buf[-32 * self.F:].view(torch.int32).view(self.F, 8)
+
+    def frame(self, f):
+        """The workspace of frame f as a single-frame `_Workspace`-like view (for export_state)."""
+        w = _Workspace.__new__(_Workspace)
+        w.buf, w.R_cap = self.buf, self.R_cap
+        w.geom, w.binning, w.img = self.geom + f * self.gs, self.binning + f * self.bs, self.img + f * self.is_
+        w.status = self.status + 32 * f
+        return w
+
+
+def _stack_settings(settings, dev):
+    views = torch.stack([_f32c(s.viewmatrix, "viewmatrix") for s in settings]).contiguous()
+    projs = torch.stack([_f32c(s.projmatrix, "projmatrix") for s in settings]).contiguous()
+    cams = torch.stack([_f32c(s.campos, "campos") for s in settings]).contiguous()
+    F = len(settings)
+    tx = (_dgm_lib.c_float * F)(*[float(s.tanfovx) for s in settings])
+    ty = (_dgm_lib.c_float * F)(*[float(s.tanfovy) for s in settings])
+    return views, projs, cams, tx, ty
+
+
+class _RasterizeGaussiansBatch(torch.autograd.Function):
+    """F frames over one set of Gaussians: colors [F,3,H,W], radii [F,P].  Gradients of the
+    Gaussian parameters are the SUM over frames (accumulated inside the kernels); means2D, if given
+    as an [F,P,3] tensor, receives the per-frame screen-space gradients."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings):
+        rs0 = settings[0]
+        F = len(settings)
+        for s in settings:
+            if (s.image_height, s.image_width, s.sh_degree, s.scale_modifier) != \
+                    (rs0.image_height, rs0.image_width, rs0.sh_degree, rs0.scale_modifier):
+                raise ValueError("all frames of a batch must share image size, SH degree and scale modifier")
+        means3D = _f32c(means3D, "means3D")
+        if means3D is None:
+            raise ValueError("means3D must have dimensions (num_points, 3)")
+        t = (_f32c(rs0.bg, "bg"), _f32c(sh, "sh"), _f32c(colors_precomp, "colors_precomp"),
+             _f32c(opacities, "opacities"), _f32c(scales, "scales"), _f32c(rotations, "rotations"),
+             _f32c(cov3Ds_precomp, "cov3D_precomp"))
+        bg, sh_, col, opac, sc, rot, cov = t
+        dev = means3D.device
+        views, projs, cams, tx, ty = _stack_settings(settings, dev)
+        P, H, W = means3D.shape[0], int(rs0.image_height), int(rs0.image_width)
+        M = int(sh_.shape[1]) if sh_ is not None else 0
+        key = (dev.index, P, W, H)
+        lib = _dgm_lib.lib()
+        p = _dgm_lib.ptr
+
+        def run(R_cap):
+            ws = _BatchWorkspace(F, P, W, H, R_cap, dev)
+            color = torch.empty((F, 3, H, W), dtype=torch.float32, device=dev)
+            radii = torch.empty((F, P), dtype=torch.int32, device=dev)
+            rc = lib.dgr_forward_batch(F, P, rs0.sh_degree, M, p(bg), W, H, p(means3D), p(sh_), p(col), p(opac),
+                                       p(sc), float(rs0.scale_modifier), p(rot), p(cov), p(views), p(projs), p(cams),
+                                       tx, ty, int(bool(rs0.prefiltered)), p(color), p(radii), ws.geom, ws.gs,
+                                       ws.binning, ws.bs, R_cap, ws.img, ws.is_, ws.status, _N_STREAMS,
+                                       _dgm_lib.stream_ptr())
+            _dgm_lib.check(rc, "dgr_forward_batch")
+            return color, radii, ws
+
+        _Sizing.poll()
+        cap = _Sizing.hint.get(key)
+        if cap is None or _SYNC or rs0.debug:
+            cap0 = cap if cap is not None else _round_cap(max(4 * P, 1 << 18))
+            color, radii, ws = run(cap0)
+            st = ws.status_tensor().cpu()
+            _Sizing.hint[key] = max(_Sizing.hint.get(key, 0), _grow(int(st[:, 0].max())))
+            if int(st[:, 1].max()):
+                color, radii, ws = run(_Sizing.hint[key])
+        else:
+            color, radii, ws = run(cap)
+            _Sizing.watch(ws.status_tensor(), key, cap)
+        ctx.ws, ctx.tensors, ctx.cams, ctx.settings = ws, t, (views, projs, cams, tx, ty), settings
+        ctx.has_m2d = means2D is not None
+        ctx.save_for_backward(means3D, radii)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _):
+        bg, sh, col, opac, sc, rot, cov = ctx.tensors
+        views, projs, cams, tx, ty = ctx.cams
+        means3D, radii = ctx.saved_tensors
+        ws, rs0 = ctx.ws, ctx.settings[0]
+        _Sizing.poll(block=True)
+        F, P = ws.F, means3D.shape[0]
+        H, W = int(rs0.image_height), int(rs0.image_width)
+        M = int(sh.shape[1]) if sh is not None else 0
+        offs, o = [], 0
+        for w in (3 * F, 1, 3, 3, 6, 3, 4, 3 * M):  # m2d[F,P,3] opac col m3d cov scale rot sh
+            offs.append(o)
+            o = (o + P * w + 3) // 4 * 4
+        flat = torch.empty((max(o, 1),), dtype=torch.float32, device=means3D.device)
+        base = flat.data_ptr()
+        ptrs = [base + 4 * x for x in offs]
+
+        def gview(i, *shape):
+            n = 1
+            for d in shape:
+                n *= d
+            return flat[offs[i]:offs[i] + n].view(*shape)
+
+        dpix = _f32c(grad_out_color, "grad_out_color")
+        p = _dgm_lib.ptr
+        rc = _dgm_lib.lib().dgr_backward_batch(
+            F, P, rs0.sh_degree, M, p(bg), W, H, p(means3D), p(sh), p(col), p(sc), float(rs0.scale_modifier), p(rot),
+            p(cov), p(views), p(projs), p(cams), tx, ty, p(radii), ws.geom, ws.gs, ws.binning, ws.bs, ws.R_cap,
+            ws.img, ws.is_, p(dpix), ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[7] if M else None, ptrs[5],
+            ptrs[6], _N_STREAMS, _dgm_lib.stream_ptr())
+        _dgm_lib.check(rc, "dgr_backward_batch")
+        return (gview(3, P, 3), gview(0, F, P, 3) if ctx.has_m2d else None,
+                gview(7, P, M, 3) if sh is not None else None, gview(2, P, 3) if col is not None else None,
+                gview(1, P, 1), gview(5, P, 3) if sc is not None else None,
+                gview(6, P, 4) if rot is not None else None, gview(4, P, 6) if cov is not None else None, None)
+
+
+def rasterize_gaussians_batch(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                              settings):
+    return _RasterizeGaussiansBatch.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                          cov3Ds_precomp, tuple(settings))
+
+
+class BatchGaussianRasterizer(nn.Module):
+    """`GaussianRasterizer` for a batch of frames (one settings tuple per frame, same image size)."""
+
+    def __init__(self, settings):
+        super().__init__()
+        self.settings = tuple(settings)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None) == (colors_precomp is None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        e = torch.Tensor([])
+        return rasterize_gaussians_batch(means3D, means2D, e if shs is None else shs,
+                                         e if colors_precomp is None else colors_precomp, opacities,
+                                         e if scales is None else scales, e if rotations is None else rotations,
+                                         e if cov3D_precomp is None else cov3D_precomp, self.settings)
 
 
 class GaussianRasterizationSettings(NamedTuple):

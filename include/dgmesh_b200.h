@@ -90,7 +90,7 @@ int dgr_forward(int P, int D, int M,
  * nine gradient outputs are fully written (zeros for culled Gaussians), the
  * caller does NOT need to zero them (the reference requires zero-filled
  * tensors, rasterize_points.cu:151-159).
- *   dL_dpix[3,H,W] -> dL_dmean2D[P,3] (.xy written, .z = 0), dL_dconic[P,4],
+ *   dL_dpix[3,H,W] -> dL_dmean2D[P,3] (.xy written, .z = 0), dL_dconic[P,4] (may be NULL),
  *   dL_dopacity[P], dL_dcolor[P,3], dL_dmean3D[P,3], dL_dcov3D[P,6],
  *   dL_dsh[P,M,3] (may be NULL when shs == NULL), dL_dscale[P,3], dL_drot[P,4] */
 int dgr_backward(int P, int D, int M,
@@ -106,6 +106,51 @@ int dgr_backward(int P, int D, int M,
                  float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
                  float* dL_dscale, float* dL_drot,
                  void* stream);
+
+/* ------------------------------------------------------------------------
+ * Frame batches (data parallelism over training frames): F cameras
+ * rendered over ONE set of Gaussians.  No reference counterpart -- the reference renders
+ * one frame per call (dgmesh/train.py:150-178); this is F x dgr_forward / dgr_backward
+ * with (a) one host call, (b) consecutive frames enqueued on alternating internal side
+ * streams forked from / joined to `stream`, so the short latency-bound kernels of frame
+ * f+1 overlap the blend kernels of frame f, and (c) parameter gradients SUMMED over the
+ * frames inside the kernels (what autograd's per-frame accumulation computes).
+ *   per-frame inputs : viewmatrices[F,16], projmatrices[F,16], cam_poses[F,3] (device);
+ *                      tan_fovx_host[F], tan_fovy_host[F] (HOST arrays)
+ *   per-frame outputs: out_color[F,3,H,W], radii[F,P], status[F,DGR_STATUS_WORDS]
+ *   workspaces       : frame f uses geom_ws + f*geom_stride, ... (each stride >= the size
+ *                      reported by dgr_workspace_sizes, multiple of 128)
+ * backward: dL_dpix[F,3,H,W] -> dL_dmean2D[F,P,3] per frame; dL_dopacity[P], dL_dcolor[P,3],
+ * dL_dmean3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscale[P,3], dL_drot[P,4] summed over
+ * frames (fully written, no zero-fill needed).  n_streams: 1..4 side streams.
+ * ------------------------------------------------------------------------ */
+int dgr_forward_batch(int F, int P, int D, int M,
+                      const float* background, int W, int H,
+                      const float* means3D, const float* shs, const float* colors_precomp,
+                      const float* opacities, const float* scales, float scale_modifier,
+                      const float* rotations, const float* cov3D_precomp,
+                      const float* viewmatrices, const float* projmatrices, const float* cam_poses,
+                      const float* tan_fovx_host, const float* tan_fovy_host, int prefiltered,
+                      float* out_color, int* radii,
+                      void* geom_ws, size_t geom_stride,
+                      void* binning_ws, size_t binning_stride, int64_t R_cap,
+                      void* img_ws, size_t img_stride,
+                      int32_t* status, int n_streams, void* stream);
+
+int dgr_backward_batch(int F, int P, int D, int M,
+                       const float* background, int W, int H,
+                       const float* means3D, const float* shs, const float* colors_precomp,
+                       const float* scales, float scale_modifier, const float* rotations,
+                       const float* cov3D_precomp,
+                       const float* viewmatrices, const float* projmatrices, const float* cam_poses,
+                       const float* tan_fovx_host, const float* tan_fovy_host, const int* radii,
+                       void* geom_ws, size_t geom_stride, void* binning_ws, size_t binning_stride,
+                       int64_t R_cap, void* img_ws, size_t img_stride,
+                       const float* dL_dpix,
+                       float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
+                       float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                       float* dL_dscale, float* dL_drot,
+                       int n_streams, void* stream);
 
 /* Frustum test, Rasterizer::markVisible (rasterizer.h:22-27,
  * rasterizer_impl.cu:54-66,141-153): present[P] (uint8 bool). */

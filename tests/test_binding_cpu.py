@@ -114,3 +114,32 @@ def test_settings_fields_match_reference_order():
         "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
         "sh_degree", "campos", "prefiltered", "debug")
     assert math.isclose(dgr._cap_from_bytes(60 * 4096 + 128), 4096)
+
+
+def test_batch_api_glue(stub, monkeypatch):
+    monkeypatch.setattr(dgr, "_sizes", lambda P, W, H, R: (4096, 60 * R + 128, 8192, 4096,
+                                                           (60 * R + 128 + 511) // 512 * 512, 8192))
+    monkeypatch.setattr(dgr._BatchWorkspace, "status_tensor",
+                        lambda self: torch.tensor([[stub.R, 0, 0, 0, 0, 0, 0, 0]] * self.F, dtype=torch.int32))
+    sc = synth.gaussian_scene(n=48, seed=2)
+    cams = [synth.look_at_camera(azimuth_deg=40.0 * k, width=32, height=32) for k in range(3)]
+    sets = [synth.raster_settings_for(c, torch.ones(3), settings_cls=dgr.GaussianRasterizationSettings) for c in cams]
+    leaves = {k: sc[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    m2d = torch.zeros(3, 48, 3, requires_grad=True)
+    color, radii = dgr.BatchGaussianRasterizer(sets)(means3D=leaves["means3D"], means2D=m2d,
+                                                     opacities=leaves["opacities"], shs=leaves["shs"],
+                                                     scales=leaves["scales"], rotations=leaves["rotations"])
+    assert color.shape == (3, 3, 32, 32) and radii.shape == (3, 48)
+    color.backward(torch.ones_like(color))
+    assert tuple(m2d.grad.shape) == (3, 48, 3) and tuple(leaves["shs"].grad.shape) == (48, 16, 3)
+    fwd = [c for c in stub.calls if c[0] == "dgr_forward_batch"][0][1]
+    assert fwd[0] == 3 and fwd[1] == 48 and len(fwd[18]) == 3           # F, P, tan_fovx host array
+    assert fwd[24] % 128 == 0 and fwd[26] % 128 == 0 and fwd[29] % 128 == 0  # workspace strides
+    bwd = [c for c in stub.calls if c[0] == "dgr_backward_batch"][0][1]
+    for ptr in bwd[28:36]:
+        assert ptr is None or ptr % 16 == 0
+    mixed = list(sets)
+    mixed[1] = mixed[1]._replace(image_width=48)
+    with pytest.raises(ValueError, match="share image size"):
+        dgr.BatchGaussianRasterizer(mixed)(means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"],
+                                           shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])

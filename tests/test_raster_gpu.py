@@ -278,3 +278,37 @@ def test_full_size_properties():
     # gradient is zero exactly for culled Gaussians
     inv = a["radii"] == 0
     assert float(a["grads"]["means3D"][inv].abs().sum()) == 0
+
+
+def test_batch_equals_per_frame():
+    """BatchGaussianRasterizer (multi-stream, in-kernel gradient accumulation) == F single-frame calls:
+    images / radii identical, parameter gradients = sum over frames."""
+    import diff_gaussian_rasterization as dgr
+    import synth
+    sc, _ = util.small_scene(n=4000, W=160, H=96, seed=6, scale=0.04)
+    sc = _cuda(sc)
+    cams = [_cam_cuda(synth.look_at_camera(azimuth_deg=20.0 + 70.0 * k, elevation_deg=10.0 + 5 * k, width=160,
+                                           height=96, fovx=0.6911, fovy=0.6911 * 96 / 160)) for k in range(4)]
+    bg = torch.tensor([0.9, 0.8, 0.7], device="cuda")
+    sets = [synth.raster_settings_for(c, bg, settings_cls=dgr.GaussianRasterizationSettings) for c in cams]
+    dpix = torch.randn(4, 3, 96, 160, generator=torch.Generator().manual_seed(5)).cuda()
+    names = ("means3D", "opacities", "scales", "rotations", "shs")
+
+    def leaves():
+        return {k: sc[k].detach().clone().requires_grad_(True) for k in names}
+
+    la = leaves()
+    m2d = torch.zeros(4, 4000, 3, device="cuda", requires_grad=True)
+    color, radii = dgr.BatchGaussianRasterizer(sets)(means3D=la["means3D"], means2D=m2d, opacities=la["opacities"],
+                                                     shs=la["shs"], scales=la["scales"], rotations=la["rotations"])
+    color.backward(dpix)
+    lb = leaves()
+    for k in range(4):
+        m2 = torch.zeros(4000, 3, device="cuda", requires_grad=True)
+        c, r = dgr.GaussianRasterizer(sets[k])(means3D=lb["means3D"], means2D=m2, opacities=lb["opacities"],
+                                               shs=lb["shs"], scales=lb["scales"], rotations=lb["rotations"])
+        assert torch.equal(c, color[k]) and torch.equal(r, radii[k]), k
+        c.backward(dpix[k])
+        assert util.rel_err(m2d.grad[k], m2.grad) < 1e-5, k
+    for n in names:
+        assert util.rel_err(la[n].grad, lb[n].grad) < 1e-5, n

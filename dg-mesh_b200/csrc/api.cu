@@ -2,6 +2,8 @@
 #include "../../include/dgmesh_b200.h"
 #include "common.cuh"
 #include "raster_kernels.h"
+#include "knn_kernels.h"
+#include "dpsr_kernels.h"
 
 #include <string.h>
 
@@ -287,6 +289,68 @@ int dgr_export_state(int P, int W, int H, int64_t R_cap, const void* geom_ws, co
   return check(dgm::launch_export_state(P, W, H, R_cap, geom_ws, binning_ws, img_ws, depths, means2D, cov3D,
                                         conic_opacity, rgb, tiles_touched, clamped, point_list_keys, point_list,
                                         ranges, final_T, n_contrib, (cudaStream_t)stream));
+}
+
+int dgk_workspace_size(int P, size_t* bytes) {
+  if (P < 0 || !bytes) return bad("dgk_workspace_size: bad argument");
+  dgm::KnnWS::from(nullptr, (size_t)P, P ? dgm::knn_cub_bytes(P) : 0, bytes);
+  return DGM_OK;
+}
+
+int dgk_dist2(int P, const float* points, float* mean_dist2, void* ws, size_t ws_bytes, void* stream) {
+  if (P < 0) return bad("dgk_dist2: negative size");
+  if (P == 0) return DGM_OK;
+  if (!points || !mean_dist2 || !ws) return bad("dgk_dist2: null pointer");
+  size_t need;
+  dgk_workspace_size(P, &need);
+  if (ws_bytes < need) {
+    strncpy(g_last_error, "dgk_dist2: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return check(dgm::launch_knn(P, points, mean_dist2, ws, (cudaStream_t)stream));
+}
+
+int dgp_plan_create(int G, void** plan, size_t* ws_bytes) {
+  if (G < 4 || (G & 1) || !plan) return bad("dgp_plan_create: G must be even and >= 4");
+  size_t work = 0;
+  if (dgm::dpsr_plan_create(G, plan, &work) != 0) {
+    strncpy(g_last_error, "dgp_plan_create: cuFFT plan creation failed", sizeof(g_last_error) - 1);
+    return DGM_E_LAUNCH;
+  }
+  if (ws_bytes) dgm::DpsrWS::from(nullptr, G, work, ws_bytes);
+  return DGM_OK;
+}
+
+int dgp_plan_destroy(void* plan) {
+  dgm::dpsr_plan_destroy(plan);
+  return DGM_OK;
+}
+
+static int dgp_check(void* plan, size_t ws_bytes, void* ws) {
+  if (!plan || !ws) return bad("dpsr: null plan / workspace");
+  size_t need;
+  dgm::DpsrWS::from(nullptr, dgm::dpsr_plan_res(plan), dgm::dpsr_plan_work(plan), &need);
+  if (ws_bytes < need) {
+    strncpy(g_last_error, "dpsr: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return DGM_OK;
+}
+
+int dgp_forward(void* plan, int N, double sig, const float* V, const float* Nrm, int mode, const float* thres,
+                float* out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = dgp_check(plan, ws_bytes, ws);
+  if (rc != DGM_OK) return rc;
+  if (N < 0 || !out || (N > 0 && (!V || !Nrm)) || (mode && !thres)) return bad("dgp_forward: bad argument");
+  return check(dgm::launch_dpsr_forward(plan, N, sig, V, Nrm, mode, thres, out, ws, (cudaStream_t)stream));
+}
+
+int dgp_backward(void* plan, int N, const float* V, const float* Nrm, int mode, const float* dL_dout, float* dV,
+                 float* dN, float* dthres, void* ws, size_t ws_bytes, void* stream) {
+  int rc = dgp_check(plan, ws_bytes, ws);
+  if (rc != DGM_OK) return rc;
+  if (N < 0 || !dL_dout || (N > 0 && (!V || !Nrm || !dV || !dN))) return bad("dgp_backward: bad argument");
+  return check(dgm::launch_dpsr_backward(plan, N, V, Nrm, mode, dL_dout, dV, dN, dthres, ws, (cudaStream_t)stream));
 }
 
 int dgm_profile_enable(int on) {

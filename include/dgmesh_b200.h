@@ -174,6 +174,39 @@ int dgr_export_state(int P, int W, int H, int64_t R_cap,
                      void* stream);
 
 /* ------------------------------------------------------------------------
+ * simple-knn: mean squared distance to the 3 nearest neighbours of every point.
+ * replaces SimpleKNN::knn / distCUDA2 (dgmesh/submodules/simple-knn/simple_knn.cu:185-221,
+ * spatial.cu:15-26, ext.cpp:15-17).  points[P,3] fp32 -> mean_dist2[P] fp32.
+ * Unlike the reference (two blocking D2H copies, simple_knn.cu:196-200) nothing
+ * synchronises with the host.
+ * ------------------------------------------------------------------------ */
+int dgk_workspace_size(int P, size_t* bytes);
+int dgk_dist2(int P, const float* points, float* mean_dist2,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * DPSR -- differentiable Poisson surface reconstruction on a G^3 periodic grid.
+ * replaces DPSR.forward (dgmesh/nvdiffrast_utils/dpsr.py:28-70) with point_rasterize /
+ * grid_interp / spec_gaussian_filter / fftfreqs (dgmesh/nvdiffrast_utils/dpsr_utils.py:25-197)
+ * and the autograd graph PyTorch builds through them.  Batch size 1 (what DG-Mesh uses).
+ *   V[N,3] in (0,1), Nrm[N,3]  ->  out[G,G,G]
+ *   mode 0: out = phi exactly as DPSR.forward returns it (shifted, scaled by -0.5/|phi[0,0,0]|)
+ *   mode 1: out = psr * sign - thres[0] as mesh_renderer forms it (dgmesh/utils/renderer.py:
+ *           163-168) without the reference's host read of psr[0,0,0,0]; thres is a device scalar
+ * The plan owns the cuFFT handles (the one-time setup the reference leaves to torch.fft's plan
+ * cache); all device memory, including the FFT work area, is the caller's workspace, which must
+ * be passed unchanged from dgp_forward to dgp_backward (it holds the field for the backward pass).
+ * backward: dL_dout[G,G,G] -> dV[N,3], dN[N,3], dthres[1] (mode 1; may be NULL).
+ * ------------------------------------------------------------------------ */
+int dgp_plan_create(int G, void** plan, size_t* ws_bytes);
+int dgp_plan_destroy(void* plan);
+int dgp_forward(void* plan, int N, double sig, const float* V, const float* Nrm, int mode,
+                const float* thres, float* out, void* ws, size_t ws_bytes, void* stream);
+int dgp_backward(void* plan, int N, const float* V, const float* Nrm, int mode,
+                 const float* dL_dout, float* dV, float* dN, float* dthres,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * Measurement hooks (bench.py roofline leg).  Off by default.  When enabled the
  * library records a CUDA event pair around each of its kernels ON THE LAUNCHING
  * STREAM; dgm_profile_read synchronises those events (the only call in this

@@ -111,3 +111,75 @@ class RasterOracle:
         if M == 0:
             g["dL_dsh"] = np.zeros((P, 0, 3), dt)
         return g
+
+
+def knn_mean_dist2(points):
+    """CPU restatement of simple-knn's contract (simple_knn.cu:147-183): for every point the mean of
+    the squared distances to its 3 nearest OTHER points (duplicates count with distance 0); fewer than
+    3 neighbours leave FLT_MAX slots exactly as the reference's initial values do."""
+    from scipy.spatial import cKDTree
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    P = pts.shape[0]
+    k = min(4, P)
+    d, _ = cKDTree(pts).query(pts, k=k)
+    d = d.reshape(P, k)[:, 1:] ** 2          # drop the point itself (distance 0 at rank 0)
+    best = np.full((P, 3), np.finfo(np.float32).max, dtype=np.float64)
+    best[:, :d.shape[1]] = d
+    with np.errstate(over="ignore"):
+        return ((best[:, 0].astype(np.float32) + best[:, 1].astype(np.float32)) + best[:, 2].astype(np.float32)) \
+            / np.float32(3.0)
+
+
+# ----------------------------------------------------------------------------- DPSR
+def _dpsr_stencil(pts, G):
+    """ind0 / ind1 / per-axis weights exactly as point_rasterize / grid_interp form them
+    (dgmesh/nvdiffrast_utils/dpsr_utils.py:158-176), in fp32."""
+    f32 = np.float32
+    cs = f32(1.0) / f32(G)
+    t = (pts.astype(f32) / cs).astype(f32)
+    fl, ce = np.floor(t), np.ceil(t)
+    i0 = fl.astype(np.int64)
+    i1 = np.fmod(ce, f32(G)).astype(np.int64)
+    xyz0, xyz1 = (fl * cs).astype(f32), ((fl + f32(1)) * cs).astype(f32)
+    w0 = (np.abs(pts.astype(f32) - xyz1) / cs).astype(f32)   # weight of node ind0: distance to the opposite corner
+    w1 = (np.abs(pts.astype(f32) - xyz0) / cs).astype(f32)
+    return i0, i1, w0, w1
+
+
+def dpsr_forward_np(V, N, G, sig):
+    """numpy restatement of DPSR.forward (dgmesh/nvdiffrast_utils/dpsr.py:28-70), batch 1:
+    V [n,3] in (0,1), N [n,3] -> phi [G,G,G] (fp32 semantics, fp64 FFT)."""
+    f32 = np.float32
+    V, N = np.asarray(V, f32), np.asarray(N, f32)
+    i0, i1, w0, w1 = _dpsr_stencil(V, G)
+    ras = np.zeros((3, G, G, G), np.float64)
+    for a in (0, 1):
+        for b in (0, 1):
+            for c in (0, 1):
+                ix, iy, iz = (i1 if a else i0)[:, 0], (i1 if b else i0)[:, 1], (i1 if c else i0)[:, 2]
+                w = ((w1 if a else w0)[:, 0] * (w1 if b else w0)[:, 1] * (w1 if c else w0)[:, 2]).astype(f32)
+                for ch in range(3):
+                    np.add.at(ras[ch], (ix, iy, iz), (w * N[:, ch]).astype(np.float64))
+    ras_s = np.fft.rfftn(ras.astype(f32), axes=(1, 2, 3))                       # dpsr.py:37
+    fx = np.fft.fftfreq(G, d=1 / G)
+    fz = np.fft.rfftfreq(G, d=1 / G)
+    om = np.stack(np.meshgrid(fx, fx, fz, indexing="ij"), -1)                   # fftfreqs, dpsr_utils.py:25-46
+    dis = np.sqrt((om ** 2).sum(-1))
+    filt = np.exp(-0.5 * ((sig * 2 * dis / G) ** 2)).astype(f32)               # spec_gaussian_filter, :58-64
+    omega = (om.astype(f32) * f32(2 * np.pi)).astype(f32)
+    Nf = ras_s * filt[None]
+    div = sum((-1j * omega[..., c]) * Nf[c] for c in range(3))                  # dpsr.py:47
+    lap = -(omega ** 2).sum(-1)
+    Phi = div / (lap + f32(1e-6))
+    Phi[0, 0, 0] = 0
+    phi = np.fft.irfftn(Phi, s=(G, G, G), axes=(0, 1, 2))                       # dpsr.py:55
+    fv = np.zeros(V.shape[0], np.float64)
+    for a in (0, 1):
+        for b in (0, 1):
+            for c in (0, 1):
+                ix, iy, iz = (i1 if a else i0)[:, 0], (i1 if b else i0)[:, 1], (i1 if c else i0)[:, 2]
+                w = (w1 if a else w0)[:, 0] * (w1 if b else w0)[:, 1] * (w1 if c else w0)[:, 2]
+                fv += phi[ix, iy, iz] * w
+    phi = phi - fv.mean()
+    fv0 = phi[0, 0, 0]
+    return (-phi / abs(fv0) * 0.5).astype(f32)

@@ -121,3 +121,42 @@ def rel_err(a, b):
     if a.numel() == 0:
         return 0.0
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def load_reference_pymodules():
+    """The reference's pure-PyTorch modules (copied to oracle/_ref/refpy by oracle/build_ref.py, or read
+    from /root/reference when present) as a package `refpy` whose unavailable third-party imports
+    (trimesh, open3d, pytorch3d, ...) are replaced by inert stand-ins: only the torch/numpy functions
+    of the hot path are exercised.  Returns None when neither location exists."""
+    if "refpy" in sys.modules:
+        return sys.modules["refpy"]
+    import types
+    from unittest import mock
+    refpy = os.path.join(REF_DIR, "refpy")
+    if not os.path.isdir(refpy):
+        return None
+    for name in ("trimesh", "imageio", "skimage", "skimage.measure", "pytorch3d", "pytorch3d.structures",
+                 "pytorch3d.renderer", "igl", "open3d", "plyfile"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = mock.MagicMock()
+    pkg = types.ModuleType("refpy")
+    pkg.__path__ = [refpy]
+    sys.modules["refpy"] = pkg
+    utils = types.ModuleType("utils")          # time_utils does `from utils.rigid_utils import exp_se3`
+    utils.__path__ = [refpy]
+    sys.modules.setdefault("utils", utils)
+    for sub in ("rigid_utils",):
+        spec = importlib.util.spec_from_file_location(f"utils.{sub}", os.path.join(refpy, f"{sub}.py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"utils.{sub}"] = m
+        spec.loader.exec_module(m)
+    for sub in ("dpsr_utils", "dpsr", "time_utils", "graphics_utils", "sh_utils"):
+        spec = importlib.util.spec_from_file_location(f"refpy.{sub}", os.path.join(refpy, f"{sub}.py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"refpy.{sub}"] = m
+        spec.loader.exec_module(m)
+        setattr(pkg, sub, m)
+    return pkg

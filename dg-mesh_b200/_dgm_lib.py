@@ -37,6 +37,10 @@ SIGNATURES = {
     "dgp_plan_destroy": (c_int, [P]),
     "dgp_forward": (c_int, [P, c_int, ctypes.c_double, P, P, c_int, P, P, P, c_size_t, P]),
     "dgp_backward": (c_int, [P, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
+    "dgmc_workspace_size": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
+    "dgmc_count": (c_int, [c_int, P, c_float, P, c_size_t, P, P]),
+    "dgmc_emit": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
+    "dgmc_backward": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
     "dgm_profile_enable": (c_int, [c_int]),
     "dgm_profile_read": (c_int, [ctypes.POINTER(c_float), c_int]),
 }

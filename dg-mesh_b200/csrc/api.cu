@@ -4,6 +4,7 @@
 #include "raster_kernels.h"
 #include "knn_kernels.h"
 #include "dpsr_kernels.h"
+#include "mc_kernels.h"
 
 #include <string.h>
 
@@ -351,6 +352,45 @@ int dgp_backward(void* plan, int N, const float* V, const float* Nrm, int mode, 
   if (rc != DGM_OK) return rc;
   if (N < 0 || !dL_dout || (N > 0 && (!V || !Nrm || !dV || !dN))) return bad("dgp_backward: bad argument");
   return check(dgm::launch_dpsr_backward(plan, N, V, Nrm, mode, dL_dout, dV, dN, dthres, ws, (cudaStream_t)stream));
+}
+
+int dgmc_workspace_size(int G, size_t* bytes) {
+  if (G < 2 || G > 1024 || !bytes) return bad("dgmc_workspace_size: bad argument");
+  dgm::McWS::from(nullptr, G, bytes);
+  return DGM_OK;
+}
+
+static int dgmc_check(int G, const float* phi, void* ws, size_t ws_bytes) {
+  if (G < 2 || G > 1024 || !phi || !ws) return bad("marching cubes: bad argument");
+  size_t need;
+  dgm::McWS::from(nullptr, G, &need);
+  if (ws_bytes < need) {
+    strncpy(g_last_error, "marching cubes: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return DGM_OK;
+}
+
+int dgmc_count(int G, const float* phi, float iso, void* ws, size_t ws_bytes, int32_t* totals, void* stream) {
+  int rc = dgmc_check(G, phi, ws, ws_bytes);
+  if (rc != DGM_OK) return rc;
+  if (!totals) return bad("dgmc_count: null totals");
+  return check(dgm::launch_mc_count(G, phi, iso, ws, totals, (cudaStream_t)stream));
+}
+
+int dgmc_emit(int G, const float* phi, float iso, void* ws, size_t ws_bytes, float* verts, int32_t* faces,
+              void* stream) {
+  int rc = dgmc_check(G, phi, ws, ws_bytes);
+  if (rc != DGM_OK) return rc;
+  return check(dgm::launch_mc_emit(G, phi, iso, ws, verts, faces, (cudaStream_t)stream));
+}
+
+int dgmc_backward(int G, const float* phi, float iso, void* ws, size_t ws_bytes, const float* dL_dverts,
+                  float* dL_dphi, void* stream) {
+  int rc = dgmc_check(G, phi, ws, ws_bytes);
+  if (rc != DGM_OK) return rc;
+  if (!dL_dphi) return bad("dgmc_backward: null output");
+  return check(dgm::launch_mc_backward(G, phi, iso, ws, dL_dverts, dL_dphi, (cudaStream_t)stream));
 }
 
 int dgm_profile_enable(int on) {

@@ -207,6 +207,25 @@ int dgp_backward(void* plan, int N, const float* V, const float* Nrm, int mode,
                  void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Differentiable marching cubes.  Stands in for diso.DiffMC.__call__(grid, deform=None,
+ * isovalue) as called at dgmesh/utils/renderer.py:171 and
+ * dgmesh/scene/gaussian_model_dpsr_dynamic_anchor.py:704,851 (third-party package, not in the
+ * reference tree: only the CONTRACT at the call sites is reproduced).
+ *   phi[G,G,G] fp32, iso  ->  verts[V,3] fp32 in [0,1]^3 (index/(G-1)), faces[F,3] int32
+ * Two-phase because V and F are data dependent: dgmc_count writes totals[2] = {V, F}
+ * (device int32); the caller reads them (the one host sync, as in the reference where diso
+ * returns exactly-sized tensors), allocates, and calls dgmc_emit with the same workspace.
+ * dgmc_backward: dL_dverts[V,3] -> dL_dphi[G,G,G] (fully written).
+ * ------------------------------------------------------------------------ */
+int dgmc_workspace_size(int G, size_t* bytes);
+int dgmc_count(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
+               int32_t* totals, void* stream);
+int dgmc_emit(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
+              float* verts, int32_t* faces, void* stream);
+int dgmc_backward(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
+                  const float* dL_dverts, float* dL_dphi, void* stream);
+
+/* ------------------------------------------------------------------------
  * Measurement hooks (bench.py roofline leg).  Off by default.  When enabled the
  * library records a CUDA event pair around each of its kernels ON THE LAUNCHING
  * STREAM; dgm_profile_read synchronises those events (the only call in this

@@ -183,3 +183,61 @@ def dpsr_forward_np(V, N, G, sig):
     phi = phi - fv.mean()
     fv0 = phi[0, 0, 0]
     return (-phi / abs(fv0) * 0.5).astype(f32)
+
+
+# ----------------------------------------------------------------------------- marching cubes
+def marching_cubes_np(phi, iso=0.0):
+    """numpy restatement of the marching-cubes contract visible at DG-Mesh's call sites
+    (dgmesh/utils/renderer.py:171): phi [G,G,G] -> verts [V,3] in [0,1]^3 (index/(G-1)), faces [F,3].
+    `diso` (the reference's third-party implementation) is unavailable: PARITY UNPINNED; the case
+    table is the derived one of tools/gen_mc_tables.py, shared with the CUDA kernels but consumed by
+    this independent, loop-based emitter.  Small grids only."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "tools"))
+    from gen_mc_tables import tables_for_python
+    ntri, tri, edge_lo = tables_for_python()
+    phi = np.asarray(phi, np.float32)
+    G = phi.shape[0]
+    inside = phi < np.float32(iso)
+    vid = {}
+    verts, faces = [], []
+
+    def vertex(i, j, k, e):
+        c, axis = int(edge_lo[e]), e // 4
+        a = (i + (c & 1), j + ((c >> 1) & 1), k + (c >> 2))
+        key = (a, axis)
+        if key not in vid:
+            b = list(a)
+            b[axis] += 1
+            p0, p1 = phi[a], phi[tuple(b)]
+            t = (np.float32(iso) - p0) / (p1 - p0)
+            pos = np.array(a, np.float32)
+            pos[axis] += t
+            vid[key] = len(verts)
+            verts.append(pos / np.float32(G - 1))
+        return vid[key]
+
+    for i in range(G - 1):
+        for j in range(G - 1):
+            for k in range(G - 1):
+                cs = 0
+                for v in range(8):
+                    if inside[i + (v & 1), j + ((v >> 1) & 1), k + (v >> 2)]:
+                        cs |= 1 << v
+                for t in range(int(ntri[cs])):
+                    faces.append([vertex(i, j, k, int(tri[cs, 3 * t + q])) for q in range(3)])
+    return (np.array(verts, np.float32).reshape(-1, 3), np.array(faces, np.int64).reshape(-1, 3))
+
+
+def mesh_topology(verts, faces):
+    """(V - E + F, all edges shared by exactly two consistently oriented faces?)"""
+    f = np.asarray(faces)
+    de = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    und = np.sort(de, axis=1)
+    uniq, cnt = np.unique(und, axis=0, return_counts=True)
+    manifold = bool(np.all(cnt == 2))
+    # orientation: every directed edge appears exactly once (its reverse belongs to the neighbour)
+    dcode = de[:, 0].astype(np.int64) * (f.max() + 1) + de[:, 1]
+    oriented = len(np.unique(dcode)) == len(dcode)
+    used = len(np.unique(f))
+    return used - len(uniq) + len(f), manifold, oriented

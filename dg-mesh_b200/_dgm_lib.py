@@ -41,6 +41,7 @@ SIGNATURES = {
     "dgmc_count": (c_int, [c_int, P, c_float, P, c_size_t, P, P]),
     "dgmc_emit": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
     "dgmc_backward": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
+    "dgl_gemm_bf16": (c_int, [c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, c_int, c_int, P]),
     "dgm_profile_enable": (c_int, [c_int]),
     "dgm_profile_read": (c_int, [ctypes.POINTER(c_float), c_int]),
 }

@@ -5,6 +5,8 @@
 #include "knn_kernels.h"
 #include "dpsr_kernels.h"
 #include "mc_kernels.h"
+#include "mlp_gemm.cuh"
+#include "mlp_kernels.h"
 
 #include <string.h>
 
@@ -391,6 +393,18 @@ int dgmc_backward(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
   if (rc != DGM_OK) return rc;
   if (!dL_dphi) return bad("dgmc_backward: null output");
   return check(dgm::launch_mc_backward(G, phi, iso, ws, dL_dverts, dL_dphi, (cudaStream_t)stream));
+}
+
+int dgl_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const float* bias, int relu,
+                  float* C, int ldc, int k_split, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return bad("dgl_gemm_bf16: bad argument");
+  if ((lda | ldb | K) & 7 || (ldc & 3)) return bad("dgl_gemm_bf16: lda/ldb/K must be multiples of 8, ldc of 4");
+  dgm::GemmArgs g = {};
+  g.A = (const __nv_bfloat16*)A; g.B = (const __nv_bfloat16*)B; g.lda = lda; g.ldb = ldb;
+  g.M = M; g.N = N; g.K = K;
+  g.k_split = (k_split > 0 && k_split < K) ? (k_split + 63) / 64 * 64 : K;
+  g.bias = bias; g.relu = relu; g.out_f32 = C; g.ld_f32 = ldc; g.atomic = g.k_split < K;
+  return check(dgm::launch_gemm(g, (cudaStream_t)stream));
 }
 
 int dgm_profile_enable(int on) {

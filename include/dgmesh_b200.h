@@ -226,6 +226,16 @@ int dgmc_backward(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
                   const float* dL_dverts, float* dL_dphi, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Tensor-core GEMM building block of the MLPs (tcgen05.mma, fp32 accumulation in TMEM):
+ *   C[M,N] (fp32, ldc) = A[M,K] (bf16, lda) * B[N,K]^T (bf16, ldb)  [+ bias[N]] [ReLU]
+ * lda, ldb, K multiples of 8; ldc multiple of 4.  Exposed for the parity tests of the
+ * building block (torch.matmul on the same bf16 operands is the oracle); the networks below
+ * drive the same kernel from inside the library.
+ * ------------------------------------------------------------------------ */
+int dgl_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                  const float* bias, int relu, float* C, int ldc, int k_split, void* stream);
+
+/* ------------------------------------------------------------------------
  * Measurement hooks (bench.py roofline leg).  Off by default.  When enabled the
  * library records a CUDA event pair around each of its kernels ON THE LAUNCHING
  * STREAM; dgm_profile_read synchronises those events (the only call in this

@@ -42,6 +42,13 @@ SIGNATURES = {
     "dgmc_emit": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
     "dgmc_backward": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
     "dgl_gemm_bf16": (c_int, [c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, c_int, c_int, P]),
+    "dgl_mlp_pack_sizes": (c_int, [ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
+    "dgl_mlp_pack": (c_int, [P, P, P, P, P]),
+    "dgl_mlp_grad_pointers": (c_int, [P, P]),
+    "dgl_mlp_unpack_grads": (c_int, [P, P, P, P]),
+    "dgl_mlp_workspace": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "dgl_mlp_forward": (c_int, [P, c_int, P, P, P, c_int, P, c_size_t, P]),
+    "dgl_mlp_backward": (c_int, [P, c_int, P, P, P, P, c_size_t, P, P, P]),
     "dgm_profile_enable": (c_int, [c_int]),
     "dgm_profile_read": (c_int, [ctypes.POINTER(c_float), c_int]),
 }
@@ -55,6 +62,34 @@ def profile_read():
     buf = (c_float * 16)()
     check(lib().dgm_profile_read(buf, 16), "dgm_profile_read")
     return {n: float(buf[i]) for i, n in enumerate(KERNEL_NAMES) if buf[i] >= 0}
+
+
+
+class DglNet(ctypes.Structure):
+    """Mirror of `struct DglNet` (include/dgmesh_b200.h)."""
+    _fields_ = [("has_timenet", c_int), ("in_t", c_int), ("n_out", c_int), ("sigmoid_out", c_int),
+                ("W", c_void_p * 8), ("WT", c_void_p * 8), ("b", c_void_p * 8),
+                ("Wh", c_void_p), ("WhT", c_void_p), ("bh", c_void_p),
+                ("Wt0", c_void_p), ("bt0", c_void_p), ("Wt1", c_void_p), ("Wt1T", c_void_p), ("bt1", c_void_p)]
+
+
+class DglRaw(ctypes.Structure):
+    """Mirror of `struct DglRaw` (reference-shaped fp32 parameters)."""
+    _fields_ = [("has_timenet", c_int), ("in_t", c_int), ("sigmoid_out", c_int), ("n_heads", c_int),
+                ("head_rows", c_int * 4), ("W", c_void_p * 8), ("b", c_void_p * 8), ("Wh", c_void_p * 4),
+                ("bh", c_void_p * 4), ("Wt0", c_void_p), ("bt0", c_void_p), ("Wt1", c_void_p), ("bt1", c_void_p)]
+
+
+class DglRawGrads(ctypes.Structure):
+    _fields_ = [("W", c_void_p * 8), ("b", c_void_p * 8), ("Wh", c_void_p * 4), ("bh", c_void_p * 4),
+                ("Wt0", c_void_p), ("bt0", c_void_p), ("Wt1", c_void_p), ("bt1", c_void_p)]
+
+
+class DglGrads(ctypes.Structure):
+    """Mirror of `struct DglGrads`."""
+    _fields_ = [("dW", c_void_p * 8), ("db", c_void_p * 8), ("dWh", c_void_p), ("dbh", c_void_p),
+                ("dWt0", c_void_p), ("dbt0", c_void_p), ("dWt1", c_void_p), ("dbt1", c_void_p)]
+
 
 _lib = None
 

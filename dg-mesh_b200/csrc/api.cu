@@ -407,6 +407,74 @@ int dgl_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, in
   return check(dgm::launch_gemm(g, (cudaStream_t)stream));
 }
 
+int dgl_mlp_pack_sizes(size_t* w_bytes, size_t* b_bytes, size_t* g_bytes) {
+  dgm::mlp_pack_sizes(w_bytes, b_bytes, g_bytes);
+  return DGM_OK;
+}
+
+static int raw_ok(const DglRaw* r) {
+  if (!r || r->n_heads < 1 || r->n_heads > 4 || r->in_t < 1 || r->in_t > 30) return 0;
+  int rows = 0;
+  for (int h = 0; h < r->n_heads; ++h) rows += r->head_rows[h];
+  return rows >= 1 && rows <= 16;
+}
+
+int dgl_mlp_pack(const DglRaw* raw, void* wbuf, float* bbuf, DglNet* net_out, void* stream) {
+  if (!raw_ok(raw) || !wbuf || !bbuf || !net_out) return bad("dgl_mlp_pack: bad argument");
+  return check(dgm::launch_mlp_pack(*raw, wbuf, bbuf, net_out, (cudaStream_t)stream));
+}
+
+int dgl_mlp_grad_pointers(float* gbuf, DglGrads* grads_out) {
+  if (!gbuf || !grads_out) return bad("dgl_mlp_grad_pointers: null pointer");
+  dgm::mlp_grad_pointers(gbuf, grads_out);
+  return DGM_OK;
+}
+
+int dgl_mlp_unpack_grads(const DglRaw* raw, const float* gbuf, const DglRawGrads* out, void* stream) {
+  if (!raw_ok(raw) || !gbuf || !out) return bad("dgl_mlp_unpack_grads: bad argument");
+  return check(dgm::launch_mlp_unpack_grads(*raw, gbuf, *out, (cudaStream_t)stream));
+}
+
+int dgl_mlp_workspace(int P, int train, size_t* bytes) {
+  if (P < 0 || !bytes) return bad("dgl_mlp_workspace: bad argument");
+  *bytes = dgm::mlp_workspace_bytes(P, train);
+  return DGM_OK;
+}
+
+static int dgl_check(const DglNet* n, int P, const void* ws, size_t ws_bytes, int train) {
+  if (!n || P <= 0 || !ws) return bad("mlp: bad argument");
+  if (n->n_out < 1 || n->n_out > 16 || n->in_t < 1 || n->in_t > 32 || !n->Wh || !n->bh) return bad("mlp: bad net");
+  for (int l = 0; l < 8; ++l)
+    if (!n->W[l] || !n->b[l]) return bad("mlp: missing layer");
+  if (n->has_timenet && (!n->Wt0 || !n->bt0 || !n->Wt1 || !n->bt1)) return bad("mlp: missing timenet");
+  if (ws_bytes < dgm::mlp_workspace_bytes(P, train)) {
+    strncpy(g_last_error, "mlp: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return DGM_OK;
+}
+
+int dgl_mlp_forward(const DglNet* net, int P, const float* x, const float* t, float* out, int train, void* ws,
+                    size_t ws_bytes, void* stream) {
+  int rc = dgl_check(net, P, ws, ws_bytes, train);
+  if (rc != DGM_OK) return rc;
+  if (!x || !t || !out) return bad("dgl_mlp_forward: null pointer");
+  return check(dgm::launch_mlp_forward(*net, P, x, t, out, train, ws, (cudaStream_t)stream));
+}
+
+int dgl_mlp_backward(const DglNet* net, int P, const float* x, const float* out, const float* g_out, void* ws,
+                     size_t ws_bytes, const DglGrads* grads, float* dx, void* stream) {
+  int rc = dgl_check(net, P, ws, ws_bytes, 1);
+  if (rc != DGM_OK) return rc;
+  if (!x || !out || !g_out || !grads) return bad("dgl_mlp_backward: null pointer");
+  for (int l = 0; l < 8; ++l)
+    if (!net->WT[l] || !grads->dW[l] || !grads->db[l]) return bad("dgl_mlp_backward: missing transposed weights / grads");
+  if (!net->WhT || !grads->dWh || !grads->dbh) return bad("dgl_mlp_backward: missing head buffers");
+  if (net->has_timenet && (!net->Wt1T || !grads->dWt0 || !grads->dbt0 || !grads->dWt1 || !grads->dbt1))
+    return bad("dgl_mlp_backward: missing timenet buffers");
+  return check(dgm::launch_mlp_backward(*net, P, x, out, g_out, ws, *grads, dx, (cudaStream_t)stream));
+}
+
 int dgm_profile_enable(int on) {
   using dgm::g_prof;
   if (on && !g_prof.ev[0][0]) {

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) mc_emit_kernel(int G, const float* __rest
   const int k = (int)(id % G), j = (int)((id / G) % G), i = (int)(id / ((size_t)G * G));
   const unsigned mask = inf >> 8, cs = inf & 0xff;
   const unsigned long long off = offsets[id];
-  const float inv = 1.0f / (float)(G - 1);
+  const float gm1 = (float)(G - 1);
   if (mask) {
     const float p0 = phi[id];
     uint32_t v = (uint32_t)(off & 0xffffffffull);
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(256) mc_emit_kernel(int G, const float* __rest
         const float t = (iso - p0) / (p1 - p0);
         float pos[3] = {base[0], base[1], base[2]};
         pos[a] += t;
-        verts[3 * (size_t)v + 0] = pos[0] * inv;
-        verts[3 * (size_t)v + 1] = pos[1] * inv;
-        verts[3 * (size_t)v + 2] = pos[2] * inv;
+        verts[3 * (size_t)v + 0] = pos[0] / gm1;  // IEEE division: identical to the numpy restatement
+        verts[3 * (size_t)v + 1] = pos[1] / gm1;
+        verts[3 * (size_t)v + 2] = pos[2] / gm1;
         ++v;
       }
     }

@@ -236,6 +236,86 @@ int dgl_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, in
                   const float* bias, int relu, float* C, int ldc, int k_split, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Deformation / appearance MLPs (dgmesh/utils/time_utils.py:58-323: DeformNetwork,
+ * DeformNetworkNormal, DeformNetworkNormalSep, AppearanceNetwork; driven through
+ * DeformModel*.step / AppearanceModel.step, dgmesh/scene/deform_model.py, appearance_model.py).
+ * The reference runs ~30 fp32 cuBLAS / elementwise kernels per call; here the whole network is a
+ * chain of bf16 tcgen05 GEMMs (fp32 accumulation) with fused bias / ReLU epilogues.
+ *
+ * DglNet describes one network with PACKED parameters (built by the host mirror, see
+ * dg-mesh_b200/utils/time_utils.py): bf16 row-major weights [out, Kpad] and their transposes
+ * [Kpad, out]; fp32 biases.  Input columns: 0..62 pe(x,10) | 63 zero | 64.. time features | zero
+ * pad to 96; the skip layer (index 5) sees those 96 columns followed by the 256 hidden units.
+ *   x[P,3], t[P] fp32  ->  out[P,16] fp32 (first n_out columns valid; column order = the
+ *   reference's heads concatenated: warp 3, rotation 4, scaling 3, normal 3 / colour 3)
+ * train != 0 additionally stores what dgl_mlp_backward needs in the workspace.
+ * backward: g_out[P,16] -> every weight / bias gradient in the packed fp32 layouts of DglGrads
+ * (fully written) and dx[P,3] (may be NULL).
+ * ------------------------------------------------------------------------ */
+typedef struct DglNet {
+  int has_timenet;   /* is_blender: pe(t,6) -> 13 -> 256 -> 30 ; else pe(t,10) = 21 features */
+  int in_t;          /* 30 or 21 */
+  int n_out;         /* <= 16 */
+  int sigmoid_out;   /* AppearanceNetwork */
+  const void* W[8];  /* bf16 [256, Kpad_l], Kpad = 96, 256 x4, 352, 256 x2 */
+  const void* WT[8]; /* bf16 [Kpad_l, 256] */
+  const float* b[8];
+  const void* Wh;    /* bf16 [16, 256] */
+  const void* WhT;   /* bf16 [256, 16] */
+  const float* bh;   /* [16] */
+  const void* Wt0;   /* bf16 [256, 16]   timenet.0 (13 -> 256), input padded to 16 */
+  const float* bt0;
+  const void* Wt1;   /* bf16 [32, 256]   timenet.2 (256 -> 30), output padded to 32 */
+  const void* Wt1T;  /* bf16 [256, 32] */
+  const float* bt1;  /* [32] */
+} DglNet;
+
+typedef struct DglGrads {
+  float* dW[8];      /* fp32 [256, Kpad_l] */
+  float* db[8];      /* [256] */
+  float* dWh;        /* [16, 256] */
+  float* dbh;        /* [16] */
+  float* dWt0;       /* [256, 16] */
+  float* dbt0;       /* [256] */
+  float* dWt1;       /* [32, 256] */
+  float* dbt1;       /* [32] */
+} DglGrads;
+
+/* Reference-shaped parameters (fp32, nn.Linear layout [out, in]); DglRawGrads has the same shape
+ * with writable pointers.  Heads are listed in output-column order (n_heads <= 4). */
+typedef struct DglRaw {
+  int has_timenet, in_t, sigmoid_out, n_heads;
+  int head_rows[4];
+  const float* W[8];   /* linear.l.weight: [256, 63+in_t], [256,256] x4, [256, 63+in_t+256], [256,256] x2 */
+  const float* b[8];
+  const float* Wh[4];  /* e.g. gaussian_warp [3,256], gaussian_rotation [4,256], ... */
+  const float* bh[4];
+  const float *Wt0, *bt0, *Wt1, *bt1;  /* timenet.0 [256,13], timenet.2 [in_t,256] */
+} DglRaw;
+typedef struct DglRawGrads {
+  float* W[8];
+  float* b[8];
+  float* Wh[4];
+  float* bh[4];
+  float *Wt0, *bt0, *Wt1, *bt1;
+} DglRawGrads;
+
+/* byte sizes of the packed bf16 weight buffer, the packed fp32 bias buffer and the packed fp32
+ * gradient buffer (fixed for this architecture) */
+int dgl_mlp_pack_sizes(size_t* w_bytes, size_t* b_bytes, size_t* g_bytes);
+/* fill wbuf / bbuf from the raw parameters and write the DglNet pointer table (host struct) */
+int dgl_mlp_pack(const DglRaw* raw, void* wbuf, float* bbuf, DglNet* net_out, void* stream);
+/* pointer table into a packed gradient buffer, and its scatter into reference-shaped tensors */
+int dgl_mlp_grad_pointers(float* gbuf, DglGrads* grads_out);
+int dgl_mlp_unpack_grads(const DglRaw* raw, const float* gbuf, const DglRawGrads* out, void* stream);
+
+int dgl_mlp_workspace(int P, int train, size_t* bytes);
+int dgl_mlp_forward(const DglNet* net, int P, const float* x, const float* t, float* out,
+                    int train, void* ws, size_t ws_bytes, void* stream);
+int dgl_mlp_backward(const DglNet* net, int P, const float* x, const float* out, const float* g_out,
+                     void* ws, size_t ws_bytes, const DglGrads* grads, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------
  * Measurement hooks (bench.py roofline leg).  Off by default.  When enabled the
  * library records a CUDA event pair around each of its kernels ON THE LAUNCHING
  * STREAM; dgm_profile_read synchronises those events (the only call in this

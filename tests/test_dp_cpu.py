@@ -1,0 +1,69 @@
+"""Frame data parallelism on CPU (gloo, world_size 2): the all-reduced flat gradient equals the sum of
+the per-frame gradients a single process computes; statistics reductions; frame sharding."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import dp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _frame_loss(params, k):
+    a, b = params
+    return ((a * (k + 1)).sin() * b[k % b.shape[0]]).sum() + (b ** 2).sum() * 0.1 * (k + 1)
+
+
+def _worker(rank, world, port, n_frames, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.randn(50, 3, requires_grad=True), torch.randn(7, 3, requires_grad=True)]
+    fg = dp.FlatGrad(params)
+    fg.zero()
+    for k in dp.shard_frames(n_frames, rank, world):
+        _frame_loss(params, k).backward()
+    flat = fg.allreduce(average=False).clone()
+    acc, den, rad = torch.full((50, 1), float(rank + 1)), torch.full((50, 1), 1.0), torch.arange(50.) * (rank + 1)
+    dp.sync_densification_stats(acc, den, rad)
+    if rank == 0:
+        out.put((flat, acc, den, rad))
+    dist.destroy_process_group()
+
+
+def test_allreduced_gradient_equals_sum_of_frame_gradients():
+    n_frames, world = 8, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    flat, acc, den, rad = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    params = [torch.randn(50, 3, requires_grad=True), torch.randn(7, 3, requires_grad=True)]
+    fg = dp.FlatGrad(params)
+    for k in range(n_frames):
+        _frame_loss(params, k).backward()
+    assert torch.allclose(flat, fg.flat, rtol=1e-5, atol=1e-6)
+    assert torch.all(acc == 3.0) and torch.all(den == 2.0) and torch.equal(rad, torch.arange(50.) * 2)
+
+
+def test_shard_frames_and_single_process_noop():
+    assert dp.shard_frames(8, 1, 4) == [1, 5] and sum(len(dp.shard_frames(8, r, 8)) for r in range(8)) == 8
+    p = [torch.ones(3, requires_grad=True)]
+    fg = dp.FlatGrad(p)
+    (p[0] * 2).sum().backward()
+    assert torch.equal(fg.allreduce(), torch.full((3,), 2.0))     # not initialised: no collective

@@ -116,8 +116,8 @@ def parse_ref_buffers(geom, binning, img, P, R, W, H):
 def rel_err(a, b):
     """max |a-b| / (max|b| + tiny): the 'relative to the tensor's scale' error used for the
     1e-4 fp32 contract (north_star)."""
-    a = torch.as_tensor(a, dtype=torch.float64)
-    b = torch.as_tensor(b, dtype=torch.float64)
+    a = torch.as_tensor(a, dtype=torch.float64).detach()
+    b = torch.as_tensor(b, dtype=torch.float64).detach()
     if a.numel() == 0:
         return 0.0
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
@@ -160,3 +160,11 @@ def load_reference_pymodules():
         spec.loader.exec_module(m)
         setattr(pkg, sub, m)
     return pkg
+
+
+def rel_l2(a, b):
+    """||a - b||_2 / ||b||_2 (the error measure for bf16 gradient tensors: single elements of a bf16
+    backward can be off by far more than the tensor as a whole)."""
+    a = torch.as_tensor(a, dtype=torch.float64).detach().cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).detach().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))

@@ -24,7 +24,7 @@ for G, n in ((32, 3000), (64, 20000)):
         phi = mod(Va[None], Na[None])[0]
         (phi * gout.to(dev)).sum().backward()
         res[name] = (phi.detach().cpu(), Na.grad.cpu(), Va.grad.cpu())
-    res["numpy"] = (torch.from_numpy(dpsr_forward_np(V.numpy(), N.numpy(), G, 3.0)), None, None)
+    res["numpy"] = (torch.from_numpy(dpsr_forward_np(V.detach().numpy(), N.detach().numpy(), G, 3.0)), None, None)
     names = list(res)
     print(f"G={G} n={n}")
     for i in range(len(names)):

@@ -29,6 +29,7 @@ namespace dgm {
 struct Stencil {
   int i0[3], i1[3];
   float w0[3], w1[3];  // weight of the lower / upper node along each axis
+  float g0[3], g1[3];  // d w0 / d p, d w1 / d p  (torch: d|x|/dx = sign(x), 0 at x == 0)
 };
 
 __device__ __forceinline__ Stencil make_stencil(const float* p, int G, float cs) {
@@ -40,9 +41,15 @@ __device__ __forceinline__ Stencil make_stencil(const float* p, int G, float cs)
     const float fl = floorf(t), ce = ceilf(t);
     s.i0[d] = (int)fl;
     s.i1[d] = (int)fmodf(ce, size);               // periodic wrap-around, :159
-    const float xyz0 = fl * cs, xyz1 = (fl + 1.0f) * cs;
-    s.w0[d] = fabsf(p[d] - xyz1) / cs;            // weight of node ind0 uses the OPPOSITE corner, :168-174
-    s.w1[d] = fabsf(p[d] - xyz0) / cs;
+    // explicit roundings: an FMA-contracted p - fl*cs keeps the unrounded product and can flip the
+    // SIGN of a ~1e-9 difference for points on grid nodes when 1/G is not a power of two
+    const float xyz0 = __fmul_rn(fl, cs), xyz1 = __fmul_rn(fl + 1.0f, cs);
+    const float d1 = __fsub_rn(p[d], xyz1), d0 = __fsub_rn(p[d], xyz0);
+    s.w0[d] = fabsf(d1) / cs;                     // weight of node ind0 uses the OPPOSITE corner, :168-174
+    s.w1[d] = fabsf(d0) / cs;
+    const float inv_cs = 1.0f / cs;
+    s.g0[d] = d1 > 0.f ? inv_cs : (d1 < 0.f ? -inv_cs : 0.f);
+    s.g1[d] = d0 > 0.f ? inv_cs : (d0 < 0.f ? -inv_cs : 0.f);  // a point exactly on a node: 0, like autograd
     s.i0[d] = min(max(s.i0[d], 0), G - 1);        // points are clamped to (0,1) by the caller
   }
   return s;
@@ -244,7 +251,6 @@ __global__ void __launch_bounds__(256) dpsr_bwd_interp_kernel(int N, int G, floa
   const float pt[3] = {V[3 * p], V[3 * p + 1], V[3 * p + 2]};
   const Stencil s = make_stencil(pt, G, cs);
   float gv[3] = {0.f, 0.f, 0.f};
-  const float inv_cs = 1.0f / cs;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int a = q >> 2, b = (q >> 1) & 1, d = q & 1;
@@ -253,10 +259,9 @@ __global__ void __launch_bounds__(256) dpsr_bwd_interp_kernel(int N, int G, floa
     const size_t cell = ((size_t)ix * G + iy) * G + iz;
     atomicAdd(&dphi[cell], c * (ux * uy * uz));
     const float ph = phi_raw[cell] * inv_n3;
-    // d|p - corner|/dp / cs: +1/cs for the upper node's weight, -1/cs for the lower node's
-    gv[0] += (a ? inv_cs : -inv_cs) * uy * uz * ph;
-    gv[1] += (b ? inv_cs : -inv_cs) * ux * uz * ph;
-    gv[2] += (d ? inv_cs : -inv_cs) * ux * uy * ph;
+    gv[0] += (a ? s.g1[0] : s.g0[0]) * uy * uz * ph;
+    gv[1] += (b ? s.g1[1] : s.g0[1]) * ux * uz * ph;
+    gv[2] += (d ? s.g1[2] : s.g0[2]) * ux * uy * ph;
   }
   dV[3 * p + 0] = c * gv[0];
   dV[3 * p + 1] = c * gv[1];
@@ -276,7 +281,6 @@ __global__ void __launch_bounds__(256) dpsr_bwd_points_kernel(int N, int G, floa
   const float nv[3] = {Nrm[3 * p], Nrm[3 * p + 1], Nrm[3 * p + 2]};
   const Stencil s = make_stencil(pt, G, cs);
   const size_t G3 = (size_t)G * G * G;
-  const float inv_cs = 1.0f / cs;
   float gn[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -290,9 +294,9 @@ __global__ void __launch_bounds__(256) dpsr_bwd_points_kernel(int N, int G, floa
     gn[1] += w * r1;
     gn[2] += w * r2;
     const float dot = nv[0] * r0 + nv[1] * r1 + nv[2] * r2;
-    gv[0] += (a ? inv_cs : -inv_cs) * uy * uz * dot;
-    gv[1] += (b ? inv_cs : -inv_cs) * ux * uz * dot;
-    gv[2] += (d ? inv_cs : -inv_cs) * ux * uy * dot;
+    gv[0] += (a ? s.g1[0] : s.g0[0]) * uy * uz * dot;
+    gv[1] += (b ? s.g1[1] : s.g0[1]) * ux * uz * dot;
+    gv[2] += (d ? s.g1[2] : s.g0[2]) * ux * uy * dot;
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {

@@ -57,7 +57,7 @@ def _raw_struct(cls, spec, tensors):
 
 class _MLPFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, spec, x, t, *params):
+    def forward(ctx, spec, train, x, t, *params):
         lib = _dgm_lib.lib()
         if not x.is_cuda:
             raise ValueError("time_utils (B200): CUDA tensors required (no CPU fallback)")
@@ -76,7 +76,7 @@ class _MLPFunction(torch.autograd.Function):
         st = _dgm_lib.stream_ptr()
         _dgm_lib.check(lib.dgl_mlp_pack(ctypes.byref(raw), wbuf.data_ptr(), bbuf.data_ptr(), ctypes.byref(net), st),
                        "dgl_mlp_pack")
-        train = int(torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)))
+        train = int(train)   # decided by the caller: grad mode is always off inside Function.forward
         nbytes = _dgm_lib.c_size_t()
         _dgm_lib.check(lib.dgl_mlp_workspace(P, train, ctypes.byref(nbytes)), "dgl_mlp_workspace")
         ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)
@@ -112,7 +112,7 @@ class _MLPFunction(torch.autograd.Function):
         rg = _raw_struct(_dgm_lib.DglRawGrads, spec, outs)
         _dgm_lib.check(lib.dgl_mlp_unpack_grads(ctypes.byref(ctx.raw), gbuf.data_ptr(), ctypes.byref(rg), st),
                        "dgl_mlp_unpack_grads")
-        return (None, dx, None) + tuple(outs)
+        return (None, None, dx, None) + tuple(outs)
 
 
 class _TimeNet(nn.Module):
@@ -164,7 +164,9 @@ class _TimeNet(nn.Module):
         return ps
 
     def _run(self, x, t):
-        out = _MLPFunction.apply(self._spec, x, t, *self._param_list())
+        params = self._param_list()
+        train = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        out = _MLPFunction.apply(self._spec, train, x, t, *params)
         cols, o = [], 0
         for _, r in self.HEADS:
             cols.append(out[:, o:o + r])

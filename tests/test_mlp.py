@@ -1,7 +1,7 @@
 """Deformation / appearance MLPs: the tcgen05 GEMM chain vs (a) a bf16-rounding restatement of the
 reference network (same rounding points as the kernels: bf16 operands, fp32 accumulate) and (b) the
 reference's own fp32 PyTorch modules (oracle/_ref/refpy/time_utils.py).  Tolerances are stated
-relative to each tensor's scale: 3e-3 against (a) forward, 2e-2 against (a) backward (the backward
+relative to each tensor's scale: 2e-3 (L2) / 1e-2 (max) against (a) forward, 2e-2 against (a) backward (the backward
 also rounds dZ to bf16), 5e-2 against the fp32 reference (the bf16 gap, reported)."""
 import importlib
 
@@ -103,7 +103,10 @@ def test_mlp_forward_backward(cls, blender, n):
         yc = theirs(x, t)
         yc = torch.cat(yc if isinstance(yc, tuple) else (yc,), -1)
     assert ya.shape == yb.shape == yc.shape
-    assert util.rel_err(ya, yb) < 3e-3, "vs bf16 restatement"
+    # max-norm: one bf16 rounding flip (2^-8) in a late activation is visible in a single output;
+    # the L2 bound is the tight one
+    assert util.rel_err(ya, yb) < 1e-2, "vs bf16 restatement (max)"
+    assert util.rel_l2(ya, yb) < 2e-3, "vs bf16 restatement (L2)"
     assert util.rel_err(ya, yc) < 5e-2, "vs fp32 reference"
     g = torch.randn(ya.shape, generator=torch.Generator().manual_seed(4)).cuda()
     ya.backward(g)

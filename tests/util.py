@@ -145,8 +145,10 @@ def load_reference_pymodules():
     pkg = types.ModuleType("refpy")
     pkg.__path__ = [refpy]
     sys.modules["refpy"] = pkg
-    utils = types.ModuleType("utils")          # time_utils does `from utils.rigid_utils import exp_se3`
-    utils.__path__ = [refpy]
+    # the reference's time_utils does `from utils.rigid_utils import exp_se3`: `utils` must resolve OUR
+    # modules first (utils.time_utils, utils.renderer) and fall through to the reference copy for the rest
+    utils = types.ModuleType("utils")
+    utils.__path__ = [os.path.join(ROOT, "dg-mesh_b200", "utils"), refpy]
     sys.modules.setdefault("utils", utils)
     for sub in ("rigid_utils",):
         spec = importlib.util.spec_from_file_location(f"utils.{sub}", os.path.join(refpy, f"{sub}.py"))

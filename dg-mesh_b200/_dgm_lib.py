@@ -9,6 +9,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdgmesh_b200.so")
+# experiments only: an alternative build of the same library (never a different implementation)
+LIB_PATH = os.environ.get("DGMESH_B200_LIB", LIB_PATH)
 
 c_void_p, c_int, c_float, c_size_t, c_int64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t,
                                                ctypes.c_int64)
@@ -51,6 +53,7 @@ SIGNATURES = {
     "dgl_mlp_backward": (c_int, [P, c_int, P, P, P, P, c_size_t, P, P, P]),
     "dgm_profile_enable": (c_int, [c_int]),
     "dgm_profile_read": (c_int, [ctypes.POINTER(c_float), c_int]),
+    "dgm_timeline_read": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_float), ctypes.POINTER(c_int), c_int]),
 }
 
 KERNEL_NAMES = ["preprocess", "tile_scan", "scatter", "sort_pack", "render_fwd", "render_bwd", "preprocess_bwd",

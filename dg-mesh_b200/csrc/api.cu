@@ -157,25 +157,57 @@ int dgr_backward(int P, int D, int M, const float* background, int W, int H, con
 }
 
 namespace {
-// internal side streams + fork/join events for the frame batches (created once per process)
+// Internal streams for the frame batches (created once per process).
+//   hi[]  high priority: the short, latency-bound kernels (preprocess / binning / sort, preprocess_bwd)
+//   lo[]  low priority : the blend kernels, each of which fills the GPU on its own; two streams,
+//         alternating frames, so the next kernel's CTAs fill the SMs while the previous one's tail drains
+// A frame's binning chain runs on hi[f % NH] and its blend kernel on lo behind an event.  The block
+// scheduler serves pending high-priority CTAs first, so the binning chains of the NEXT frames slip
+// through while the blend kernel of the current frame is running (they are latency-bound and cost
+// the issue-bound blend kernel almost nothing) instead of queueing behind its 2 500 CTAs.
 struct BatchStreams {
-  cudaStream_t s[4] = {};
-  cudaEvent_t fork = nullptr, join[4] = {}, chain[2] = {};
+  static const int NH = 4;
+  cudaStream_t hi[NH] = {}, lo[2] = {};
+  cudaEvent_t fork = nullptr, done_hi[NH] = {}, done_lo[2] = {}, ready[NH] = {}, blended[2] = {};
   bool ok = false;
   bool init() {
     if (ok) return true;
-    for (int i = 0; i < 4; ++i) {
-      if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) return false;
-      if (cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return false;
+    for (int i = 0; i < NH; ++i) {
+      if (cudaStreamCreateWithPriority(&hi[i], cudaStreamNonBlocking, greatest) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&done_hi[i], cudaEventDisableTiming) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming) != cudaSuccess) return false;
     }
     if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
-    for (int i = 0; i < 2; ++i)
-      if (cudaEventCreateWithFlags(&chain[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    for (int i = 0; i < 2; ++i) {
+      if (cudaStreamCreateWithPriority(&lo[i], cudaStreamNonBlocking, least) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&done_lo[i], cudaEventDisableTiming) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&blended[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
     ok = true;
     return true;
   }
 };
+// one set per device would be needed for multi-device processes; this library is used one process per GPU
 BatchStreams g_bs;
+
+dgm::FwdArgs fwd_args(int P, int D, int M, const float* background, int W, int H, const float* means3D,
+                      const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+                      float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                      const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                      float tan_fovy, int prefiltered, float* out_color, int* radii, void* geom_ws, void* binning_ws,
+                      int64_t R_cap, void* img_ws, int32_t* status) {
+  dgm::FwdArgs a;
+  a.P = P; a.D = D; a.M = M; a.background = background; a.W = W; a.H = H;
+  a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
+  a.scales = scales; a.scale_modifier = scale_modifier; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+  a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+  a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.prefiltered = prefiltered;
+  a.out_color = out_color; a.radii = radii;
+  a.geom_ws = geom_ws; a.binning_ws = binning_ws; a.img_ws = img_ws; a.R_cap = R_cap; a.status = status;
+  return a;
+}
 }  // namespace
 
 int dgr_forward_batch(int F, int P, int D, int M, const float* background, int W, int H, const float* means3D,
@@ -193,31 +225,54 @@ int dgr_forward_batch(int F, int P, int D, int M, const float* background, int W
     strncpy(g_last_error, "dgr_forward_batch: workspace stride too small / unaligned", sizeof(g_last_error) - 1);
     return DGM_E_WORKSPACE;
   }
-  const int NS = n_streams < 1 ? 1 : (n_streams > 4 ? 4 : n_streams);
   cudaStream_t main_s = (cudaStream_t)stream;
-  const bool multi = NS > 1 && F > 1 && P > 0;
-  if (multi) {
-    if (!g_bs.init()) return check(cudaGetLastError());
-    cudaEventRecord(g_bs.fork, main_s);
-    for (int i = 0; i < NS; ++i) cudaStreamWaitEvent(g_bs.s[i], g_bs.fork, 0);
+  const bool multi = n_streams > 1 && F > 1 && P > 0;
+  const int NH = multi ? (n_streams > BatchStreams::NH ? BatchStreams::NH : n_streams) : 0;
+  if (!multi) {
+    int rc = DGM_OK;
+    for (int f = 0; f < F && rc == DGM_OK; ++f)
+      rc = dgr_forward(P, D, M, background, W, H, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
+                       rotations, cov3D_precomp, viewmatrices + 16 * f, projmatrices + 16 * f, cam_poses + 3 * f,
+                       tan_fovx_host[f], tan_fovy_host[f], prefiltered, out_color + (size_t)f * 3 * W * H,
+                       radii ? radii + (size_t)f * P : nullptr, (char*)geom_ws + f * geom_stride, geom_stride,
+                       (char*)binning_ws + f * binning_stride, binning_stride, R_cap, (char*)img_ws + f * img_stride,
+                       img_stride, status + f * DGR_STATUS_WORDS, main_s);
+    return rc;
   }
-  int rc = DGM_OK;
-  for (int f = 0; f < F && rc == DGM_OK; ++f) {
-    cudaStream_t s = multi ? g_bs.s[f % NS] : main_s;
-    rc = dgr_forward(P, D, M, background, W, H, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
-                     rotations, cov3D_precomp, viewmatrices + 16 * f, projmatrices + 16 * f, cam_poses + 3 * f,
-                     tan_fovx_host[f], tan_fovy_host[f], prefiltered, out_color + (size_t)f * 3 * W * H,
-                     radii ? radii + (size_t)f * P : nullptr, (char*)geom_ws + f * geom_stride, geom_stride,
-                     (char*)binning_ws + f * binning_stride, binning_stride, R_cap, (char*)img_ws + f * img_stride,
-                     img_stride, status + f * DGR_STATUS_WORDS, s);
+  if (!background || !out_color || !status || !means3D || !opacities) return bad("dgr_forward_batch: null required pointer");
+  if ((shs == nullptr) == (colors_precomp == nullptr)) return bad("dgr_forward_batch: exactly one of shs / colors_precomp");
+  if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+    return bad("dgr_forward_batch: exactly one of scales+rotations / cov3D_precomp");
+  if (shs && (M <= 0 || M > 16 || (D + 1) * (D + 1) > M || D < 0 || D > 3))
+    return bad("dgr_forward_batch: SH degree / coefficient count");
+  if (!g_bs.init()) return check(cudaGetLastError());
+  cudaEventRecord(g_bs.fork, main_s);
+  for (int i = 0; i < NH; ++i) cudaStreamWaitEvent(g_bs.hi[i], g_bs.fork, 0);
+  for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(g_bs.lo[i], g_bs.fork, 0);
+  cudaError_t e = cudaSuccess;
+  for (int f = 0; f < F && e == cudaSuccess; ++f) {
+    const int i = f % NH;
+    cudaStream_t lo = g_bs.lo[f & 1];
+    const dgm::FwdArgs a = fwd_args(
+        P, D, M, background, W, H, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
+        cov3D_precomp, viewmatrices + 16 * f, projmatrices + 16 * f, cam_poses + 3 * f, tan_fovx_host[f],
+        tan_fovy_host[f], prefiltered, out_color + (size_t)f * 3 * W * H, radii ? radii + (size_t)f * P : nullptr,
+        (char*)geom_ws + f * geom_stride, (char*)binning_ws + f * binning_stride, R_cap,
+        (char*)img_ws + f * img_stride, status + f * DGR_STATUS_WORDS);
+    e = dgm::launch_binning(a, g_bs.hi[i]);
+    cudaEventRecord(g_bs.ready[i], g_bs.hi[i]);
+    cudaStreamWaitEvent(lo, g_bs.ready[i], 0);
+    if (e == cudaSuccess) e = dgm::launch_render(a, lo);
   }
-  if (multi) {
-    for (int i = 0; i < NS; ++i) {
-      cudaEventRecord(g_bs.join[i], g_bs.s[i]);
-      cudaStreamWaitEvent(main_s, g_bs.join[i], 0);
-    }
+  for (int i = 0; i < NH; ++i) {
+    cudaEventRecord(g_bs.done_hi[i], g_bs.hi[i]);
+    cudaStreamWaitEvent(main_s, g_bs.done_hi[i], 0);
   }
-  return rc != DGM_OK ? rc : check(cudaGetLastError());
+  for (int i = 0; i < 2; ++i) {
+    cudaEventRecord(g_bs.done_lo[i], g_bs.lo[i]);
+    cudaStreamWaitEvent(main_s, g_bs.done_lo[i], 0);
+  }
+  return check(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 int dgr_backward_batch(int F, int P, int D, int M, const float* background, int W, int H, const float* means3D,
@@ -235,20 +290,21 @@ int dgr_backward_batch(int F, int P, int D, int M, const float* background, int 
       !geom_ws || !binning_ws || !img_ws || !dL_dpix || !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D ||
       !dL_dcov3D || !dL_dscale || !dL_drot || (shs && !dL_dsh))
     return bad("dgr_backward_batch: null required pointer");
-  // two streams suffice: render_bwd(f+1) overlaps preprocess_bwd(f); the preprocess_bwd kernels are
-  // chained by events because they accumulate into the same gradient buffers
+  // render_bwd kernels serialise on the low-priority stream; every preprocess_bwd goes to ONE
+  // high-priority stream (they accumulate into the same buffers, so they must stay ordered) and
+  // overlaps the render_bwd of the next frame
   const bool multi = n_streams > 1 && F > 1;
   cudaStream_t main_s = (cudaStream_t)stream;
+  cudaStream_t s_pp = main_s;
   if (multi) {
     if (!g_bs.init()) return check(cudaGetLastError());
+    s_pp = g_bs.hi[0];
     cudaEventRecord(g_bs.fork, main_s);
-    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(g_bs.s[i], g_bs.fork, 0);
+    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(g_bs.lo[i], g_bs.fork, 0);
+    cudaStreamWaitEvent(s_pp, g_bs.fork, 0);
   }
-  const unsigned gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
-  (void)gx; (void)gy;
   cudaError_t e = cudaSuccess;
   for (int f = 0; f < F && e == cudaSuccess; ++f) {
-    cudaStream_t s = multi ? g_bs.s[f & 1] : main_s;
     dgm::BwdArgs a;
     a.P = P; a.D = D; a.M = M; a.background = background; a.W = W; a.H = H;
     a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales;
@@ -263,15 +319,21 @@ int dgr_backward_batch(int F, int P, int D, int M, const float* background, int 
     a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D;
     a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
     a.accumulate = f > 0;
-    // the accumulating kernel of frame f must follow that of frame f-1
-    e = dgm::launch_backward_split(a, s, (multi && f > 0) ? g_bs.chain[(f - 1) & 1] : nullptr,
-                                   multi ? g_bs.chain[f & 1] : nullptr);
+    cudaStream_t s_blend = multi ? g_bs.lo[f & 1] : main_s;
+    e = dgm::launch_render_bwd(a, s_blend);
+    if (multi) {
+      cudaEventRecord(g_bs.blended[f & 1], s_blend);
+      cudaStreamWaitEvent(s_pp, g_bs.blended[f & 1], 0);
+    }
+    if (e == cudaSuccess) e = dgm::launch_preprocess_bwd(a, s_pp);
   }
   if (multi) {
     for (int i = 0; i < 2; ++i) {
-      cudaEventRecord(g_bs.join[i], g_bs.s[i]);
-      cudaStreamWaitEvent(main_s, g_bs.join[i], 0);
+      cudaEventRecord(g_bs.done_lo[i], g_bs.lo[i]);
+      cudaStreamWaitEvent(main_s, g_bs.done_lo[i], 0);
     }
+    cudaEventRecord(g_bs.done_hi[0], s_pp);
+    cudaStreamWaitEvent(main_s, g_bs.done_hi[0], 0);
   }
   return check(e != cudaSuccess ? e : cudaGetLastError());
 }
@@ -482,9 +544,24 @@ int dgm_profile_enable(int on) {
       for (int j = 0; j < 2; ++j)
         if (cudaEventCreate(&g_prof.ev[k][j]) != cudaSuccess) return check(cudaGetLastError());
   }
-  g_prof.on = on != 0;
+  g_prof.on = on;
+  g_prof.tl_n = 0;
   for (int k = 0; k < DGM_K_COUNT; ++k) g_prof.used[k] = false;
   return DGM_OK;
+}
+
+int dgm_timeline_read(float* begin_ms, float* end_ms, int* kernel_ids, int cap) {
+  using dgm::g_prof;
+  if (!begin_ms || !end_ms || !kernel_ids || cap < 0) return bad("dgm_timeline_read: bad argument");
+  if (cudaDeviceSynchronize() != cudaSuccess) return check(cudaGetLastError());
+  const int n = g_prof.tl_n < cap ? g_prof.tl_n : cap;
+  for (int i = 0; i < n; ++i) {
+    kernel_ids[i] = g_prof.tl_id[i];
+    cudaEventElapsedTime(&begin_ms[i], g_prof.tl_ev[0][0], g_prof.tl_ev[i][0]);
+    cudaEventElapsedTime(&end_ms[i], g_prof.tl_ev[0][0], g_prof.tl_ev[i][1]);
+  }
+  cudaGetLastError();
+  return n;
 }
 
 int dgm_profile_read(float* ms_host, int n) {

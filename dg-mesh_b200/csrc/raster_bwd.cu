@@ -28,19 +28,15 @@ namespace dgm {
 // values) instead of 2 x 9 x 5 = 90 for naive per-value reductions.
 // On return, for lanes with (lane & 1) == 0: r8 = total of value ((lane>>1)&7) of Gaussian
 // (lane>>4); r9 = total of value 8 of Gaussian (lane>>4) on every lane.
-__device__ __forceinline__ void warp_reduce_pair(const float (&vA)[9], const float (&vB)[9], unsigned lane, float& r8,
+__device__ __forceinline__ void warp_reduce_pair(const float (&vK)[9], const float (&vS)[9], unsigned lane, float& r8,
                                                  float& r9) {
+  // vK: the 9 values of the Gaussian this lane's half KEEPS (A on lanes 0-15, B on lanes 16-31),
+  // vS: those of the Gaussian it SENDS to the other half -- arranged by the caller, so the first
+  // (widest) butterfly stage needs no selects
   const unsigned FULL = 0xffffffffu;
   float a[8];
-  {
-    const bool up = lane & 16;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float send = up ? vA[k] : vB[k];
-      const float keep = up ? vB[k] : vA[k];
-      a[k] = keep + __shfl_xor_sync(FULL, send, 16);
-    }
-  }
+  for (int k = 0; k < 8; ++k) a[k] = vK[k] + __shfl_xor_sync(FULL, vS[k], 16);
   float b[4];
   {
     const bool up = lane & 8;
@@ -70,13 +66,7 @@ __device__ __forceinline__ void warp_reduce_pair(const float (&vA)[9], const flo
   }
   d += __shfl_xor_sync(FULL, d, 1);
   r8 = d;
-  float e;
-  {
-    const bool up = lane & 16;
-    const float send = up ? vA[8] : vB[8];
-    const float keep = up ? vB[8] : vA[8];
-    e = keep + __shfl_xor_sync(FULL, send, 16);
-  }
+  float e = vK[8] + __shfl_xor_sync(FULL, vS[8], 16);
   e += __shfl_xor_sync(FULL, e, 8);
   e += __shfl_xor_sync(FULL, e, 4);
   e += __shfl_xor_sync(FULL, e, 2);
@@ -84,7 +74,7 @@ __device__ __forceinline__ void warp_reduce_pair(const float (&vA)[9], const flo
   r9 = e;
 }
 
-__global__ void __launch_bounds__(256, 3) render_bwd_kernel(
+__global__ void __launch_bounds__(256, 4) render_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const float4* __restrict__ inst_geo,
     const float4* __restrict__ inst_attr,
     int W, int H, const float* __restrict__ bg_color, const float* __restrict__ final_Ts,
@@ -241,12 +231,17 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(
           accum1 = fmaf(a_eff, d1, accum1);
           accum2 = fmaf(a_eff, d2, accum2);
         }
-        // moments of w for both records at once (packed)
+        // moments of w for both records at once (packed).  Component .x is the record this lane's half
+        // keeps in the reduction (A on lanes 0-15, B on lanes 16-31), .y the one it hands over.
         float v[2][9];
         {
-          const float2 w2 = make_float2(wq[0], wq[1]), at2 = make_float2(atq[0], atq[1]);
-          const float2 wx = __fmul2_rn(w2, dx2), wy = __fmul2_rn(w2, dy2);
-          const float2 wxx = __fmul2_rn(wx, dx2), wxy = __fmul2_rn(wx, dy2), wyy = __fmul2_rn(wy, dy2);
+          const bool up = lane & 16;
+          const float2 w2 = up ? make_float2(wq[1], wq[0]) : make_float2(wq[0], wq[1]);
+          const float2 at2 = up ? make_float2(atq[1], atq[0]) : make_float2(atq[0], atq[1]);
+          const float2 ex2 = up ? make_float2(dx2.y, dx2.x) : dx2;
+          const float2 ey2 = up ? make_float2(dy2.y, dy2.x) : dy2;
+          const float2 wx = __fmul2_rn(w2, ex2), wy = __fmul2_rn(w2, ey2);
+          const float2 wxx = __fmul2_rn(wx, ex2), wxy = __fmul2_rn(wx, ey2), wyy = __fmul2_rn(wy, ey2);
           const float2 c0 = __fmul2_rn(at2, make_float2(dLp0, dLp0)), c1 = __fmul2_rn(at2, make_float2(dLp1, dLp1)),
                        c2 = __fmul2_rn(at2, make_float2(dLp2, dLp2));
           v[0][0] = w2.x, v[1][0] = w2.y;
@@ -606,31 +601,40 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
   }
 }
 
-cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s) { return launch_backward_split(a, s, nullptr, nullptr); }
+cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s) {
+  cudaError_t e = launch_render_bwd(a, s);
+  return e != cudaSuccess ? e : launch_preprocess_bwd(a, s);
+}
 
-cudaError_t launch_backward_split(const BwdArgs& a, cudaStream_t s, cudaEvent_t wait_before_pp,
-                                  cudaEvent_t record_after_pp) {
+// gradient of the alpha-compositing (fills the GPU); leaves the per-Gaussian moments in grad_acc
+cudaError_t launch_render_bwd(const BwdArgs& a, cudaStream_t s) {
   if (a.P == 0) return cudaSuccess;
   const unsigned gx = (a.W + TILE_X - 1) / TILE_X, gy = (a.H + TILE_Y - 1) / TILE_Y;
   const int T = gx * gy;
   GeomWS g = GeomWS::from((char*)a.geom_ws, a.P);
   ImgWS im = ImgWS::from((char*)a.img_ws, (size_t)a.W * a.H, T);
   BinWS b = BinWS::from((char*)a.binning_ws, (size_t)a.R_cap);
-  const float focal_y = a.H / (2.0f * a.tan_fovy);
-  const float focal_x = a.W / (2.0f * a.tan_fovx);
-  const int* radii = a.radii ? a.radii : g.radii;
   g_prof.begin(5, s);
   render_bwd_kernel<<<T, 256, 0, s>>>(im.ranges, im.tile_order, b.inst_geo, b.inst_attr, a.W, a.H, a.background,
                                       im.final_T, im.n_contrib, a.dL_dpix, g.grad_acc);
   g_prof.end(5, s);
-  if (wait_before_pp) cudaStreamWaitEvent(s, wait_before_pp, 0);
+  return cudaGetLastError();
+}
+
+// chain rule from the moments to the inputs (short); with a.accumulate it adds to the outputs, so
+// the calls of a frame batch must be ordered (same stream)
+cudaError_t launch_preprocess_bwd(const BwdArgs& a, cudaStream_t s) {
+  if (a.P == 0) return cudaSuccess;
+  GeomWS g = GeomWS::from((char*)a.geom_ws, a.P);
+  const float focal_y = a.H / (2.0f * a.tan_fovy);
+  const float focal_x = a.W / (2.0f * a.tan_fovx);
+  const int* radii = a.radii ? a.radii : g.radii;
   g_prof.begin(6, s);
   preprocess_bwd_kernel<<<(a.P + 127) / 128, 128, 0, s>>>(
       a.P, a.D, a.M, a.means3D, radii, a.shs, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix,
       a.projmatrix, focal_x, focal_y, a.tan_fovx, a.tan_fovy, a.cam_pos, g, a.dL_dmean2D, a.dL_dconic, a.dL_dopacity,
       a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D, a.dL_dsh, a.dL_dscale, a.dL_drot, a.accumulate);
   g_prof.end(6, s);
-  if (record_after_pp) cudaEventRecord(record_after_pp, s);
   return cudaGetLastError();
 }
 

@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __rest
 // (semantics of renderCUDA, forward.cu:261-374).
 #define RB 256  // records per batch (== reference BLOCK_SIZE staging granularity)
 
-__global__ void __launch_bounds__(256) render_fwd_kernel(const uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(256, 5) render_fwd_kernel(const uint2* __restrict__ ranges,
                                                          const uint32_t* __restrict__ tile_order,
                                                          const float4* __restrict__ inst_geo,
                                                          const float4* __restrict__ inst_attr, int W, int H,
@@ -634,6 +634,12 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 // ------------------------------------------------------------ launchers ----
 cudaError_t launch_forward(const FwdArgs& a, cudaStream_t s) {
+  cudaError_t e = launch_binning(a, s);
+  return e != cudaSuccess ? e : launch_render(a, s);
+}
+
+// preprocess + per-tile binning / sort / record packing: short, latency-bound kernels
+cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
   const unsigned gx = (a.W + TILE_X - 1) / TILE_X, gy = (a.H + TILE_Y - 1) / TILE_Y;
   const int T = gx * gy;
   GeomWS g = GeomWS::from((char*)a.geom_ws, a.P);
@@ -663,6 +669,15 @@ cudaError_t launch_forward(const FwdArgs& a, cudaStream_t s) {
   g_prof.begin(3, s);
   tile_sort_pack_kernel<<<T, 256, 0, s>>>(im.ranges, b.keys, im.hist, g, a.colors_precomp, b, a.status);
   g_prof.end(3, s);
+  return cudaGetLastError();
+}
+
+// the alpha-compositing kernel (fills the GPU)
+cudaError_t launch_render(const FwdArgs& a, cudaStream_t s) {
+  const unsigned gx = (a.W + TILE_X - 1) / TILE_X, gy = (a.H + TILE_Y - 1) / TILE_Y;
+  const int T = gx * gy;
+  ImgWS im = ImgWS::from((char*)a.img_ws, (size_t)a.W * a.H, T);
+  BinWS b = BinWS::from((char*)a.binning_ws, (size_t)a.R_cap);
   g_prof.begin(4, s);
   render_fwd_kernel<<<T, 256, 0, s>>>(im.ranges, im.tile_order, b.inst_geo, b.inst_attr, a.W, a.H, a.background,
                                       im.final_T, im.n_contrib, a.out_color, a.status);

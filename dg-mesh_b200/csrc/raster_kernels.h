@@ -40,17 +40,27 @@ struct BwdArgs {
 
 // event pairs around kernels (see dgm_profile_enable in include/dgmesh_b200.h)
 struct Profiler {
-  bool on = false;
+  int on = 0;  // 1: last duration per kernel id;  2: timeline (every launch since enable, any stream)
   cudaEvent_t ev[16][2] = {};
   bool used[16] = {};
+  static const int TL_CAP = 512;
+  cudaEvent_t tl_ev[TL_CAP][2] = {};
+  int tl_id[TL_CAP] = {};
+  int tl_n = 0;
   void begin(int k, cudaStream_t s) {
-    if (on) cudaEventRecord(ev[k][0], s);
+    if (on == 1) cudaEventRecord(ev[k][0], s);
+    if (on == 2 && tl_n < TL_CAP) {
+      if (!tl_ev[tl_n][0]) cudaEventCreate(&tl_ev[tl_n][0]), cudaEventCreate(&tl_ev[tl_n][1]);
+      tl_id[tl_n] = k;
+      cudaEventRecord(tl_ev[tl_n][0], s);
+    }
   }
   void end(int k, cudaStream_t s) {
-    if (on) {
+    if (on == 1) {
       cudaEventRecord(ev[k][1], s);
       used[k] = true;
     }
+    if (on == 2 && tl_n < TL_CAP) cudaEventRecord(tl_ev[tl_n++][1], s);
   }
 };
 extern Profiler g_prof;
@@ -58,7 +68,10 @@ extern Profiler g_prof;
 cudaError_t launch_forward(const FwdArgs& a, cudaStream_t s);
 cudaError_t launch_backward(const BwdArgs& a, cudaStream_t s);
 // same, with an event to wait on before / to record after the (accumulating) per-Gaussian kernel
-cudaError_t launch_backward_split(const BwdArgs& a, cudaStream_t s, cudaEvent_t wait_before_pp, cudaEvent_t record_after_pp);
+cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s);
+cudaError_t launch_render(const FwdArgs& a, cudaStream_t s);
+cudaError_t launch_render_bwd(const BwdArgs& a, cudaStream_t s);
+cudaError_t launch_preprocess_bwd(const BwdArgs& a, cudaStream_t s);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, uint8_t* present,
                                 cudaStream_t s);
 cudaError_t launch_export_state(int P, int W, int H, int64_t R_cap, const void* geom_ws, const void* binning_ws,

@@ -333,6 +333,12 @@ int dgl_mlp_backward(const DglNet* net, int P, const float* x, const float* out,
 #define DGM_K_COUNT 16
 int dgm_profile_enable(int on);
 int dgm_profile_read(float* ms_host, int n);
+/* dgm_profile_enable(2) = timeline mode: every rasterizer kernel launched afterwards (any stream,
+ * including the internal streams of the _batch calls) is bracketed by timing events.
+ * dgm_timeline_read synchronises the device and returns the number of launches recorded;
+ * begin/end are milliseconds relative to the first recorded launch ("begin" = the launch reached
+ * the front of its stream).  Diagnostic only (tools/batch_timeline.py). */
+int dgm_timeline_read(float* begin_ms, float* end_ms, int* kernel_ids, int cap);
 
 #ifdef __cplusplus
 }

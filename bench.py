@@ -109,7 +109,7 @@ def run_frames(dgr, synth, leaves, cams, dpix, bg, frame_ids, staged=None):
     for k in frame_ids:
         cam = cams[k]
         if staged is not None:
-            ev, view, proj, cpos, dp = staged[k]
+            ev, view, proj, cpos, dp = staged[k]   # dp: callable(color) -> pixel gradient
             torch.cuda.current_stream().wait_event(ev)
         else:
             view, proj, cpos, dp = cam.world_view_transform, cam.full_proj_transform, cam.camera_center, dpix[k]
@@ -121,48 +121,74 @@ def run_frames(dgr, synth, leaves, cams, dpix, bg, frame_ids, staged=None):
         color, radii = dgr.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d,
                                                   opacities=leaves["opacities"], shs=leaves["shs"],
                                                   scales=leaves["scales"], rotations=leaves["rotations"])
-        color.backward(dp)
+        color.backward(dp(color) if callable(dp) else dp)
         last = color
     return last
 
 
 class HostFeed:
-    """e2e leg: every step the frames' cameras (35 floats each) and pixel gradients (3xHxW fp32, standing
-    in for the ground-truth images a training step uploads) are copied from PINNED HOST memory on a side
-    stream, overlapped with rendering; the step's result (a checksum of the accumulated gradient) is
-    read back to the host."""
+    """e2e leg: every step the frames' cameras (35 floats each) and their ground-truth images (3xHxW
+    uint8, as a dataset stores them) are copied from PINNED HOST memory on a side stream, overlapped
+    with rendering; the pixel gradient is the L2-loss gradient (render - gt) formed on the device; the
+    step's result (a checksum of the accumulated parameter gradient) is copied back to the host every
+    step and read one step later (the usual lagged loss read of a training loop), the last one after
+    the final synchronise."""
 
-    def __init__(self, cams, dpix, frames, dev):
+    def __init__(self, cams, frames, dev):
         self.frames = frames
         F = len(frames)
         self.h_cam = torch.stack([torch.cat([cams[k].world_view_transform.cpu().reshape(-1),
                                              cams[k].full_proj_transform.cpu().reshape(-1),
                                              cams[k].camera_center.cpu().reshape(-1)]) for k in frames]).pin_memory()
-        self.h_dpix = torch.stack([dpix[k].cpu() for k in frames]).pin_memory()
+        g = torch.Generator().manual_seed(7)
+        self.h_gt = torch.randint(0, 256, (F, 3, HEIGHT, WIDTH), dtype=torch.uint8, generator=g).pin_memory()
         self.d_cam = torch.empty_like(self.h_cam, device=dev)
-        self.d_dpix = torch.empty_like(self.h_dpix, device=dev)
+        self.d_gt = torch.empty_like(self.h_gt, device=dev)
         self.views = [self.d_cam[i, 0:16].view(4, 4) for i in range(F)]
         self.projs = [self.d_cam[i, 16:32].view(4, 4) for i in range(F)]
         self.campos = [self.d_cam[i, 32:35] for i in range(F)]
-        self.ev_cam, self.ev_dpix, self.consumed = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.ev_cam, self.ev_gt, self.consumed = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.consumed.record()
-        self.out_host = torch.zeros(1).pin_memory()
-        self.h2d_bytes = (self.h_cam.numel() + self.h_dpix.numel()) * 4
+        self.out_host = torch.zeros(2).pin_memory()
+        self.out_ev = [None, None]
+        self.n = 0
+        self.results = []
+        self.h2d_bytes = self.h_cam.numel() * 4 + self.h_gt.numel()
 
     def upload(self):
         self.copy_stream.wait_event(self.consumed)  # the previous step no longer reads the staging buffers
         with torch.cuda.stream(self.copy_stream):
             self.d_cam.copy_(self.h_cam, non_blocking=True)
             self.ev_cam.record(self.copy_stream)
-            self.d_dpix.copy_(self.h_dpix, non_blocking=True)
-            self.ev_dpix.record(self.copy_stream)
+            self.d_gt.copy_(self.h_gt, non_blocking=True)
+            self.ev_gt.record(self.copy_stream)
+
+    def pixel_grad(self, color, i=None):
+        """d(L2 loss)/d(color) for the whole batch (i is None) or frame slot i."""
+        torch.cuda.current_stream().wait_event(self.ev_gt)
+        gt = self.d_gt if i is None else self.d_gt[i]
+        return torch.sub(color.detach(), gt.to(torch.float32).mul_(1.0 / 255.0))
 
     def finish(self, result):
         self.consumed.record()
-        self.out_host.copy_(result.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the host now holds the step's result
-        return float(self.out_host[0])
+        slot = self.n & 1
+        if self.out_ev[slot] is not None:      # the result of step n-2 has long arrived: read it
+            self.out_ev[slot].synchronize()
+            self.results.append(float(self.out_host[slot]))
+        self.out_host[slot:slot + 1].copy_(result.reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.out_ev[slot] = ev
+        self.n += 1
+
+    def drain(self):
+        torch.cuda.synchronize()
+        for slot in ((self.n & 1), ((self.n + 1) & 1)):
+            if self.out_ev[slot] is not None:
+                self.results.append(float(self.out_host[slot]))
+                self.out_ev[slot] = None
+        return self.results
 
 
 def batch_settings(dgr, cams, bg, frames, views=None, projs=None, campos=None):
@@ -177,16 +203,14 @@ def batch_settings(dgr, cams, bg, frames, views=None, projs=None, campos=None):
     return out
 
 
-def run_batch(dgr, leaves, settings, dpix_stacked, wait_fwd=None, wait_bwd=None):
+def run_batch(dgr, leaves, settings, dpix_stacked, wait_fwd=None):
     """forward + backward of a frame batch through BatchGaussianRasterizer (this repo's batched API)."""
     if wait_fwd is not None:
         torch.cuda.current_stream().wait_event(wait_fwd)
     color, radii = dgr.BatchGaussianRasterizer(settings)(
         means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"], shs=leaves["shs"],
         scales=leaves["scales"], rotations=leaves["rotations"])
-    if wait_bwd is not None:
-        torch.cuda.current_stream().wait_event(wait_bwd)
-    color.backward(dpix_stacked)
+    color.backward(dpix_stacked(color) if callable(dpix_stacked) else dpix_stacked)
     return color
 
 
@@ -292,7 +316,7 @@ def main():
     value = FRAMES * a.steps / (ms * 1e-3)
 
     # ---- e2e leg: host buffers, copies inside the timed region
-    feed = HostFeed(cams, dpix, my_frames, dev)
+    feed = HostFeed(cams, my_frames, dev)
     if ours:
         feed_settings = batch_settings(dgr, cams, bg, my_frames, feed.views, feed.projs, feed.campos)
 
@@ -300,18 +324,19 @@ def main():
         feed.upload()
         gflat.zero_()
         if ours:
-            run_batch(dgr, leaves, feed_settings, feed.d_dpix, wait_fwd=feed.ev_cam, wait_bwd=feed.ev_dpix)
+            run_batch(dgr, leaves, feed_settings, feed.pixel_grad, wait_fwd=feed.ev_cam)
         else:
-            torch.cuda.current_stream().wait_event(feed.ev_dpix)
-            staged = {k: (feed.ev_dpix, feed.views[i], feed.projs[i], feed.campos[i], feed.d_dpix[i])
-                      for i, k in enumerate(my_frames)}
+            staged = {k: (feed.ev_cam, feed.views[i], feed.projs[i], feed.campos[i],
+                          (lambda c, i=i: feed.pixel_grad(c, i))) for i, k in enumerate(my_frames)}
             run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged)
         if world > 1:
             dist.all_reduce(gflat)
         feed.finish(gflat.sum())
 
-    e2e_steps = max(3, a.steps // 2)
+    e2e_steps = a.steps
     ms_e2e = timed(step_e2e, e2e_steps, 3, world)
+    host_results = feed.drain()
+    assert len(host_results) == e2e_steps + 3 and all(math.isfinite(v) for v in host_results), host_results
     e2e_value = FRAMES * e2e_steps / (ms_e2e * 1e-3)
     h2d = feed.h2d_bytes * world
     d2h = 4 * world

@@ -193,15 +193,36 @@ __global__ void __launch_bounds__(256) sigmoid_kernel(int n, float* __restrict__
   if (i < n) y[i] = 1.f / (1.f + expf(-y[i]));
 }
 
-// column sums of a bf16 matrix [rows, ld] -> db[ncols] (fp32 atomics); threads = columns
+// column sums of a bf16 matrix [rows, ld] -> db[ncols] (fp32 atomics).  CTA = 256-row slab; a thread
+// owns 8 adjacent columns (one 16-byte load per row) and every (256 / column-groups)-th row; partial
+// sums meet in shared memory, one atomic per column per CTA.  ncols multiple of 8, <= 256.
+#define COLSUM_ROWS 256
 __global__ void __launch_bounds__(256) colsum_kernel(int rows, int ncols, int ld, const __nv_bfloat16* __restrict__ Z,
                                                      float* __restrict__ db) {
-  const int c = threadIdx.x;
-  if (c >= ncols) return;
-  const int r0 = blockIdx.x * 512, r1 = min(rows, r0 + 512);
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) s += __bfloat162float(Z[(size_t)r * ld + c]);
-  atomicAdd(&db[c], s);
+  __shared__ float s_sum[256];
+  const int groups = ncols >> 3;                 // column groups of 8
+  const int lanes = 256 / groups;                // row lanes per column group
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  s_sum[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (rl < lanes) {
+    const int r0 = blockIdx.x * COLSUM_ROWS, r1 = min(rows, r0 + COLSUM_ROWS);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      const uint4 v = *reinterpret_cast<const uint4*>(Z + (size_t)r * ld + cg * 8);
+      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(p2[q]);
+        acc[2 * q] += f.x;
+        acc[2 * q + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(&s_sum[cg * 8 + q], acc[q]);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < ncols) atomicAdd(&db[threadIdx.x], s_sum[threadIdx.x]);
 }
 
 // dE[:, 64:64+30] (fp32) -> dZt1 [Pp, 32] bf16 (+ transposed)
@@ -297,7 +318,7 @@ cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const fl
   MlpBufs b = MlpBufs::carve_all((char*)ws, P, 1, nullptr);
   const int Pp = b.Pp;
   typedef const __nv_bfloat16* CB;
-  const int rb = (Pp + 511) / 512;
+  const int rb = (Pp + COLSUM_ROWS - 1) / COLSUM_ROWS;
   cudaMemsetAsync(b.dE, 0, sizeof(float) * (size_t)Pp * K0, s);
   for (int l = 0; l < 8; ++l) {
     const int K = (l == 0) ? K0 : (l == 5 ? K5 : WID);

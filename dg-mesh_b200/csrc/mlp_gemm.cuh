@@ -4,7 +4,7 @@
 //   D[M,N] = A[M,K] * B[N,K]^T          A, B row-major bf16 (K contiguous), fp32 accumulate
 //
 // One CTA (4 warps) owns a 128 x BN output tile: operands are staged global -> shared with 16-byte
-// cp.async copies straight into the UMMA core-matrix layout (umma.cuh), 3-stage ring; ONE thread
+// cp.async copies straight into the UMMA core-matrix layout (umma.cuh), 2-stage ring; ONE thread
 // issues the tcgen05.mma instructions (M=128, N=BN, K=16) and commits each stage to an mbarrier;
 // after the last commit the four warps read their 32 TMEM lanes (tcgen05.ld 32x32b.x32) and run the
 // fused epilogue: + bias, ReLU, ReLU-mask (for dZ = dA * [act > 0]), then any of: fp32 store,
@@ -35,7 +35,7 @@ struct GemmArgs {
 
 #define GEMM_BM 128
 #define GEMM_BK 64
-#define GEMM_STAGES 3
+#define GEMM_STAGES 2  // 2 x (16 + 32) KB at BN = 256: two CTAs per SM, one's epilogue overlaps the other's main loop
 
 template <int BN>
 __global__ void __launch_bounds__(128) gemm_tn_kernel(const GemmArgs g) {
@@ -90,18 +90,20 @@ __global__ void __launch_bounds__(128) gemm_tn_kernel(const GemmArgs g) {
   };
 
   constexpr uint32_t IDESC = umma::instr_desc_bf16(GEMM_BM, BN < 16 ? 16 : BN);
-  if (nk > 0) load_chunk(0);
-  umma::cp_async_commit();
-  if (nk > 1) load_chunk(1);
-  umma::cp_async_commit();
+  // prologue: chunks 0 .. STAGES-2 in flight (one commit group per chunk, empty groups keep the count uniform)
+#pragma unroll
+  for (int c = 0; c < GEMM_STAGES - 1; ++c) {
+    if (c < nk) load_chunk(c);
+    umma::cp_async_commit();
+  }
   for (int c = 0; c < nk; ++c) {
-    if (c + 2 < nk) {
-      // stage (c+2)%3 was last read by the MMAs of chunk c-1: wait for their commit
+    const int cn = c + GEMM_STAGES - 1;  // chunk to prefetch; its stage was last read by the MMAs of chunk c-1
+    if (cn < nk) {
       if (c >= 1) mbar_wait(&s_bar[(c - 1) % GEMM_STAGES], ((c - 1) / GEMM_STAGES) & 1);
-      load_chunk(c + 2);
+      load_chunk(cn);
     }
     umma::cp_async_commit();
-    umma::cp_async_wait<2>();  // chunk c has landed (at most chunks c+1, c+2 in flight)
+    umma::cp_async_wait<GEMM_STAGES - 1>();  // chunk c has landed (at most STAGES-1 younger groups in flight)
     umma::fence_smem_to_async();
     __syncthreads();
     if (tid == 0) {

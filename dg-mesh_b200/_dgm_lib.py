@@ -43,7 +43,9 @@ SIGNATURES = {
     "dgmc_count": (c_int, [c_int, P, c_float, P, c_size_t, P, P]),
     "dgmc_emit": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
     "dgmc_backward": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
-    "dgl_gemm_bf16": (c_int, [c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, c_int, c_int, P]),
+    "dgl_gemm_ws_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "dgl_gemm_bf16": (c_int, [c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, c_int, P, c_size_t, P]),
+    "dgl_gemm_tn_bf16": (c_int, [c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, c_int, P, c_size_t, P]),
     "dgl_mlp_pack_sizes": (c_int, [ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
     "dgl_mlp_pack": (c_int, [P, P, P, P, P]),
     "dgl_mlp_grad_pointers": (c_int, [P, P]),

@@ -5,7 +5,6 @@
 #include "knn_kernels.h"
 #include "dpsr_kernels.h"
 #include "mc_kernels.h"
-#include "mlp_gemm.cuh"
 #include "mlp_kernels.h"
 
 #include <string.h>
@@ -457,16 +456,32 @@ int dgmc_backward(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
   return check(dgm::launch_mc_backward(G, phi, iso, ws, dL_dverts, dL_dphi, (cudaStream_t)stream));
 }
 
+int dgl_gemm_ws_bytes(int M, int N, int K, size_t* bytes) {
+  if (M <= 0 || N <= 0 || K <= 0 || !bytes) return bad("dgl_gemm_ws_bytes: bad argument");
+  *bytes = dgm::gemm_test_ws_bytes(M, N > 256 ? N : 256, K);
+  return DGM_OK;
+}
+
 int dgl_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const float* bias, int relu,
-                  float* C, int ldc, int k_split, void* stream) {
-  if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return bad("dgl_gemm_bf16: bad argument");
-  if ((lda | ldb | K) & 7 || (ldc & 3)) return bad("dgl_gemm_bf16: lda/ldb/K must be multiples of 8, ldc of 4");
-  dgm::GemmArgs g = {};
-  g.A = (const __nv_bfloat16*)A; g.B = (const __nv_bfloat16*)B; g.lda = lda; g.ldb = ldb;
-  g.M = M; g.N = N; g.K = K;
-  g.k_split = (k_split > 0 && k_split < K) ? (k_split + 63) / 64 * 64 : K;
-  g.bias = bias; g.relu = relu; g.out_f32 = C; g.ld_f32 = ldc; g.atomic = g.k_split < K;
-  return check(dgm::launch_gemm(g, (cudaStream_t)stream));
+                  float* C, int ldc, void* ws, size_t ws_bytes, void* stream) {
+  if (M <= 0 || N <= 0 || N > 256 || K <= 0 || !A || !B || !C || !ws) return bad("dgl_gemm_bf16: bad argument");
+  if (ldc < (N + 3) / 4 * 4 || (ldc & 3)) return bad("dgl_gemm_bf16: ldc must be a multiple of 4 and >= N rounded up to 4");
+  if (ws_bytes < dgm::gemm_test_ws_bytes(M, 256, K)) {
+    strncpy(g_last_error, "dgl_gemm_bf16: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return check(dgm::launch_gemm_test(M, N, K, A, lda, B, ldb, bias, relu, C, ldc, ws, (cudaStream_t)stream));
+}
+
+int dgl_gemm_tn_bf16(int P, int Mf, int Nf, const void* X, int ldx, const void* Y, int ldy, float* C, int ldc,
+                     int transpose_out, void* ws, size_t ws_bytes, void* stream) {
+  if (P <= 0 || Mf <= 0 || Mf > 256 || Nf <= 0 || Nf > 256 || !X || !Y || !C || !ws)
+    return bad("dgl_gemm_tn_bf16: bad argument");
+  if (ws_bytes < dgm::gemm_test_ws_bytes(P, 256, 256)) {
+    strncpy(g_last_error, "dgl_gemm_tn_bf16: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return check(dgm::launch_gemm_tn_test(P, Mf, Nf, X, ldx, Y, ldy, C, ldc, transpose_out, ws, (cudaStream_t)stream));
 }
 
 int dgl_mlp_pack_sizes(size_t* w_bytes, size_t* b_bytes, size_t* g_bytes) {

@@ -1,106 +1,118 @@
 // mlp.cu -- deformation / appearance MLPs on the tcgen05 tensor cores.
-// (first part: the GEMM building block and its C-ABI test entry; the network follows below)
-#include "mlp_gemm.cuh"
-#include "mlp_kernels.h"
-
-namespace dgm {
-
-template <int BN>
-static cudaError_t launch_gemm_bn(const GemmArgs& g, cudaStream_t s) {
-  static bool attr = false;
-  constexpr int smem = GEMM_STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2);
-  if (!attr) {
-    cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
-  const int splits = (g.K + g.k_split - 1) / g.k_split;
-  dim3 grid((g.M + GEMM_BM - 1) / GEMM_BM, (g.N + BN - 1) / BN, splits);
-  gemm_tn_kernel<BN><<<grid, 128, smem, s>>>(g);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t s) {
-  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaSuccess;
-  if (g.N <= 32) return launch_gemm_bn<32>(g, s);
-  if (g.N <= 64) return launch_gemm_bn<64>(g, s);
-  if (g.N <= 128) return launch_gemm_bn<128>(g, s);
-  return launch_gemm_bn<256>(g, s);
-}
-
-}  // namespace dgm
-
-namespace dgm {
-
-// =====================================================================================
+//
 // The networks (dgmesh/utils/time_utils.py): DeformNetwork / DeformNetworkNormal /
 // DeformNetworkNormalSep / AppearanceNetwork share one trunk --
 //   x_emb = pe(x, 10) [63], t_emb = pe(t, 6) [13] -> timenet 13->256->30 (is_blender)
 //                            or pe(t, 10) [21]                       (otherwise)
 //   h = [x_emb, t_emb] -> 8 x (Linear + ReLU), width 256, [x_emb, t_emb] re-concatenated after
 //   layer 4 (time_utils.py:178-188) -> linear heads (13 / 3 / 10 outputs, sigmoid for colour)
-// -- and run here as a chain of tcgen05 GEMMs with fused bias/ReLU epilogues over bf16
-// activations (fp32 accumulation).  Activation layout (Pp = P rounded up to 128):
-//   A5 [Pp, 352] : cols 0..62 x_emb | 63: 0 | 64..64+in_t-1 t features | ..95: 0 | 96..351 h4
-//   (layer 0 reads A5[:, :96]; the skip layer reads all 352 columns: no concat copy)
-// For training every activation is also stored TRANSPOSED ([features, Pp]) because the weight
-// gradient dW = dZ^T . H is a GEMM whose contraction runs over the points.
-// =====================================================================================
+// -- and run here as a chain of the two GEMM kernels of mlp_gemm.cuh over BLOCKED bf16 activations
+// (layout: mlp_gemm.cuh).  Activation buffers, Pp = P rounded up to 128 rows:
+//   A5 [Pp, 352] : features 0..62 x_emb | 63: 0 | 64..64+in_t-1 time features | ..95: 0 | 96..351 h4
+//                  (layer 0 reads the first 12 kbs; the skip layer reads all 44: no concat copy)
+//   T0 [Pp, 16], T1 [Pp, 256] (timenet), H[l] [Pp, 256]
+// Training keeps every activation (they double as the MN-major operands of the weight-gradient
+// GEMMs -- no transposed copies); inference ping-pongs two buffers.
+#include "mlp_gemm.cuh"
+#include "mlp_kernels.h"
+
+namespace dgm {
 
 #define XE 63      // x embedding width
-#define TCOL 64    // first column of the time features
+#define TCOL 64    // first feature of the time block
 #define K0 96      // padded width of [x_emb, t features]
 #define K5 352     // skip layer input width
 #define WID 256
 
+static int g_sms = 0;
+static int sm_count() {
+  if (!g_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+cudaError_t launch_layer_gemm(const LayerArgs& g, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layer_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_SMEM);
+    attr = true;
+  }
+  if (g.tiles <= 0) return cudaSuccess;
+  layer_gemm_kernel<<<min(g.tiles, sm_count()), LG_THREADS, LG_SMEM, s>>>(g);
+  return cudaGetLastError();
+}
+
+// X has 256 features (two 128-feature halves -> grid.y = 2)
+cudaError_t launch_dw_gemm(const DwArgs& g, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+    attr = true;
+  }
+  if (g.tiles <= 0) return cudaSuccess;
+  dim3 grid(min(g.tiles, max(1, sm_count() / 2)), 2);
+  dw_gemm_kernel<<<grid, DW_THREADS, DW_SMEM, s>>>(g);
+  return cudaGetLastError();
+}
+
 struct MlpBufs {
-  __nv_bfloat16 *A5, *T0, *T1, *H[8];        // H[4] aliases A5 + 96 (ld 352)
-  __nv_bfloat16 *A5T, *T0T, *T1T, *HT[8];    // transposed copies (training only); HT[4] = A5T + 96*Pp
-  __nv_bfloat16 *dZ[2], *dZT[2], *dZh, *dZhT, *dZt1, *dZt1T;
-  float* dE;                                  // [Pp, 96] gradient w.r.t. the embedded inputs
-  int Pp;
+  __nv_bfloat16 *A5, *T0, *T1, *H[8];  // H[4] = A5 viewed from kb 12
+  __nv_bfloat16 *dZ[2], *dZh, *dZt1;
+  float* dE;                            // [Pp, 96] fp32 row-major: gradient w.r.t. the embedded inputs
+  int Pp, tiles;
   static MlpBufs carve_all(char* base, int P, int train, size_t* bytes) {
     char* p = base;
     MlpBufs b;
-    const size_t Pp = ((size_t)P + 127) / 128 * 128;
+    const size_t Pp = ((size_t)P + ACT_R - 1) / ACT_R * ACT_R;
     b.Pp = (int)Pp;
+    b.tiles = (int)(Pp / ACT_R);
     b.A5 = carve<__nv_bfloat16>(p, Pp * K5);
     b.T0 = carve<__nv_bfloat16>(p, Pp * 16);
     b.T1 = carve<__nv_bfloat16>(p, Pp * WID);
     if (train) {
-      for (int l = 0; l < 8; ++l) b.H[l] = (l == 4) ? b.A5 + K0 : carve<__nv_bfloat16>(p, Pp * WID);
-      b.A5T = carve<__nv_bfloat16>(p, Pp * K5);
-      b.T0T = carve<__nv_bfloat16>(p, Pp * 16);
-      b.T1T = carve<__nv_bfloat16>(p, Pp * WID);
-      for (int l = 0; l < 8; ++l) b.HT[l] = (l == 4) ? b.A5T + (size_t)K0 * Pp : carve<__nv_bfloat16>(p, Pp * WID);
-      for (int i = 0; i < 2; ++i) {
-        b.dZ[i] = carve<__nv_bfloat16>(p, Pp * WID);
-        b.dZT[i] = carve<__nv_bfloat16>(p, Pp * WID);
-      }
+      for (int l = 0; l < 8; ++l) b.H[l] = (l == 4) ? b.A5 : carve<__nv_bfloat16>(p, Pp * WID);
+      for (int i = 0; i < 2; ++i) b.dZ[i] = carve<__nv_bfloat16>(p, Pp * WID);
       b.dZh = carve<__nv_bfloat16>(p, Pp * 16);
-      b.dZhT = carve<__nv_bfloat16>(p, Pp * 16);
       b.dZt1 = carve<__nv_bfloat16>(p, Pp * 32);
-      b.dZt1T = carve<__nv_bfloat16>(p, Pp * 32);
       b.dE = carve<float>(p, Pp * K0);
     } else {
       __nv_bfloat16* ping = carve<__nv_bfloat16>(p, Pp * WID);
       __nv_bfloat16* pong = carve<__nv_bfloat16>(p, Pp * WID);
-      for (int l = 0; l < 8; ++l) b.H[l] = (l == 4) ? b.A5 + K0 : ((l & 1) ? pong : ping);
-      b.A5T = b.T0T = b.T1T = nullptr;
-      for (int l = 0; l < 8; ++l) b.HT[l] = nullptr;
-      b.dZ[0] = b.dZ[1] = b.dZT[0] = b.dZT[1] = b.dZh = b.dZhT = b.dZt1 = b.dZt1T = nullptr;
+      for (int l = 0; l < 8; ++l) b.H[l] = (l == 4) ? b.A5 : ((l & 1) ? pong : ping);
+      b.dZ[0] = b.dZ[1] = b.dZh = b.dZt1 = nullptr;
       b.dE = nullptr;
     }
     if (bytes) *bytes = size_t(p - base) + 128;
     return b;
   }
+  // blocked views
+  BlkView h(int l) const {  // output of layer l
+    return (l == 4) ? BlkView{A5, (size_t)K5 * ACT_R, K0 / 8} : BlkView{H[l], (size_t)WID * ACT_R, 0};
+  }
+  BlkView a5() const { return BlkView{A5, (size_t)K5 * ACT_R, 0}; }
 };
 
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 pk;
+  __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) p2[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+  return pk;
+}
+// address of the 16-byte unit (row, kb) of a blocked activation with F features
+__device__ __forceinline__ uint4* blk_unit(__nv_bfloat16* base, int F, int row, int kb) {
+  return reinterpret_cast<uint4*>(base + (size_t)(row / ACT_R) * F * ACT_R + ((size_t)kb * ACT_R + row % ACT_R) * 8);
+}
+
 // positional encodings (time_utils.py:8-55): [v, sin(v 2^0), cos(v 2^0), ..., sin(v 2^(L-1)), cos(v 2^(L-1))]
-// One thread per point; writes bf16 rows of A5 (x part + direct time features) and T0 (timenet input).
+// One thread per row (padding rows get zeros); writes the x block (+ direct time features) of A5 and T0.
 __global__ void __launch_bounds__(256) pe_kernel(int P, int Pp, const float* __restrict__ x,
                                                  const float* __restrict__ t, int has_timenet, int t_freqs,
-                                                 __nv_bfloat16* __restrict__ A5, __nv_bfloat16* __restrict__ T0,
-                                                 __nv_bfloat16* __restrict__ A5T, __nv_bfloat16* __restrict__ T0T) {
+                                                 __nv_bfloat16* __restrict__ A5, __nv_bfloat16* __restrict__ T0) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Pp) return;
   const bool ok = p < P;
@@ -138,54 +150,37 @@ __global__ void __launch_bounds__(256) pe_kernel(int P, int Pp, const float* __r
       for (int i = 0; i < 21; ++i) e[TCOL + i] = te[i];
     }
   }
-  __nv_bfloat16* row = A5 + (size_t)p * K5;
+  const int nkb = has_timenet ? TCOL / 8 : K0 / 8;  // with a timenet its GEMM writes kbs 8..11
 #pragma unroll
-  for (int i = 0; i < K0; i += 8) {
-    if (has_timenet && i >= TCOL) break;  // the time-feature columns are written by the timenet GEMM
-    uint4 pk;
-    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) p2[q] = __floats2bfloat162_rn(e[i + 2 * q], e[i + 2 * q + 1]);
-    *reinterpret_cast<uint4*>(row + i) = pk;
-  }
+  for (int kb = 0; kb < K0 / 8; ++kb)
+    if (kb < nkb) *blk_unit(A5, K5, p, kb) = pack8(e + 8 * kb);
   if (has_timenet) {
-    uint4 pk[2];
-    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) p2[q] = __floats2bfloat162_rn(te[2 * q], te[2 * q + 1]);
-    reinterpret_cast<uint4*>(T0 + (size_t)p * 16)[0] = pk[0];
-    reinterpret_cast<uint4*>(T0 + (size_t)p * 16)[1] = pk[1];
-  }
-  if (A5T) {
-    const int n_x = has_timenet ? TCOL : K0;
-    for (int i = 0; i < n_x; ++i) A5T[(size_t)i * Pp + p] = __float2bfloat16_rn(e[i]);
-    A5T[(size_t)94 * Pp + p] = __float2bfloat16_rn(0.f);  // pad rows the timenet GEMM never writes
-    A5T[(size_t)95 * Pp + p] = __float2bfloat16_rn(0.f);
-    if (has_timenet)
-      for (int i = 0; i < 16; ++i) T0T[(size_t)i * Pp + p] = __float2bfloat16_rn(te[i]);
+    *blk_unit(T0, 16, p, 0) = pack8(te);
+    *blk_unit(T0, 16, p, 1) = pack8(te + 8);
   }
 }
 
-// gradient of the heads' pre-activation: dZh = g (* y (1 - y) for the sigmoid colour head), bf16 + transposed
+// gradient of the heads' pre-activation: dZh = g (* y (1 - y) for the sigmoid colour head), blocked [Pp,16]
 __global__ void __launch_bounds__(256) head_grad_kernel(int P, int Pp, int n_out, int sigmoid,
                                                         const float* __restrict__ g, const float* __restrict__ y,
-                                                        __nv_bfloat16* __restrict__ dZh,
-                                                        __nv_bfloat16* __restrict__ dZhT) {
+                                                        __nv_bfloat16* __restrict__ dZh) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Pp) return;
+  float v[16];
+#pragma unroll
   for (int o = 0; o < 16; ++o) {
-    float v = 0.f;
+    float w = 0.f;
     if (p < P && o < n_out) {
-      v = g[(size_t)p * 16 + o];
+      w = g[(size_t)p * 16 + o];
       if (sigmoid) {
         const float yy = y[(size_t)p * 16 + o];
-        v *= yy * (1.f - yy);
+        w *= yy * (1.f - yy);
       }
     }
-    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-    dZh[(size_t)p * 16 + o] = b;
-    dZhT[(size_t)o * Pp + p] = b;
+    v[o] = w;
   }
+  *blk_unit(dZh, 16, p, 0) = pack8(v);
+  *blk_unit(dZh, 16, p, 1) = pack8(v + 8);
 }
 
 __global__ void __launch_bounds__(256) sigmoid_kernel(int n, float* __restrict__ y) {
@@ -193,48 +188,43 @@ __global__ void __launch_bounds__(256) sigmoid_kernel(int n, float* __restrict__
   if (i < n) y[i] = 1.f / (1.f + expf(-y[i]));
 }
 
-// column sums of a bf16 matrix [rows, ld] -> db[ncols] (fp32 atomics).  CTA = 256-row slab; a thread
-// owns 8 adjacent columns (one 16-byte load per row) and every (256 / column-groups)-th row; partial
-// sums meet in shared memory, one atomic per column per CTA.  ncols multiple of 8, <= 256.
-#define COLSUM_ROWS 256
-__global__ void __launch_bounds__(256) colsum_kernel(int rows, int ncols, int ld, const __nv_bfloat16* __restrict__ Z,
-                                                     float* __restrict__ db) {
+// column sums of a blocked bf16 activation with F features (F/8 kbs) -> db[F] (fp32 atomics).
+// One CTA per row tile; a thread owns one kb and every (256 / kbs)-th row (16-byte loads).
+__global__ void __launch_bounds__(256) colsum_blk_kernel(int F, const __nv_bfloat16* __restrict__ Z,
+                                                         float* __restrict__ db) {
   __shared__ float s_sum[256];
-  const int groups = ncols >> 3;                 // column groups of 8
-  const int lanes = 256 / groups;                // row lanes per column group
-  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  const int kbs = F >> 3, lanes = 256 / kbs;
+  const int kb = threadIdx.x / lanes, rl = threadIdx.x % lanes;
   s_sum[threadIdx.x] = 0.f;
   __syncthreads();
-  if (rl < lanes) {
-    const int r0 = blockIdx.x * COLSUM_ROWS, r1 = min(rows, r0 + COLSUM_ROWS);
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int r = r0 + rl; r < r1; r += lanes) {
-      const uint4 v = *reinterpret_cast<const uint4*>(Z + (size_t)r * ld + cg * 8);
-      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const __nv_bfloat16* tile = Z + (size_t)blockIdx.x * F * ACT_R + (size_t)kb * KB_ELEMS;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = rl; r < ACT_R; r += lanes) {
+    const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)r * 8);
+    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f = __bfloat1622float2(p2[q]);
-        acc[2 * q] += f.x;
-        acc[2 * q + 1] += f.y;
-      }
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = __bfloat1622float2(p2[q]);
+      acc[2 * q] += f.x;
+      acc[2 * q + 1] += f.y;
     }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) atomicAdd(&s_sum[cg * 8 + q], acc[q]);
   }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) atomicAdd(&s_sum[kb * 8 + q], acc[q]);
   __syncthreads();
-  if ((int)threadIdx.x < ncols) atomicAdd(&db[threadIdx.x], s_sum[threadIdx.x]);
+  if ((int)threadIdx.x < F) atomicAdd(&db[threadIdx.x], s_sum[threadIdx.x]);
 }
 
-// dE[:, 64:64+30] (fp32) -> dZt1 [Pp, 32] bf16 (+ transposed)
+// dE[:, 64:96] (fp32 row-major) -> dZt1 blocked [Pp, 32] (features >= n_t are zero)
 __global__ void __launch_bounds__(256) tfeat_grad_kernel(int Pp, int n_t, const float* __restrict__ dE,
-                                                         __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZT) {
+                                                         __nv_bfloat16* __restrict__ dZ) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Pp) return;
-  for (int o = 0; o < 32; ++o) {
-    const __nv_bfloat16 b = __float2bfloat16_rn(o < n_t ? dE[(size_t)p * K0 + TCOL + o] : 0.f);
-    dZ[(size_t)p * 32 + o] = b;
-    dZT[(size_t)o * Pp + p] = b;
-  }
+  float v[32];
+#pragma unroll
+  for (int o = 0; o < 32; ++o) v[o] = (o < n_t) ? dE[(size_t)p * K0 + TCOL + o] : 0.f;
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) *blk_unit(dZ, 32, p, kb) = pack8(v + 8 * kb);
 }
 
 // dx = dE . d pe(x) / dx
@@ -258,67 +248,63 @@ __global__ void __launch_bounds__(256) pe_backward_kernel(int P, const float* __
   }
 }
 
-static GemmArgs gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K) {
-  GemmArgs g = {};
-  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.k_split = K;
+#define CK(call)                      \
+  do {                                \
+    cudaError_t e_ = (call);          \
+    if (e_ != cudaSuccess) return e_; \
+  } while (0)
+
+typedef const __nv_bfloat16* CB;
+
+static LayerArgs layer(const BlkView& A, int K, CB B, int N, int tiles) {
+  LayerArgs g = {};
+  g.A = A; g.K = K; g.B = B; g.N = N; g.tiles = tiles;
   return g;
 }
-
-#define CK(call)                        \
-  do {                                  \
-    cudaError_t e_ = (call);            \
-    if (e_ != cudaSuccess) return e_;   \
-  } while (0)
 
 cudaError_t launch_mlp_forward(const DglNet& n, int P, const float* x, const float* t, float* out, int train,
                                void* ws, cudaStream_t s) {
   MlpBufs b = MlpBufs::carve_all((char*)ws, P, train, nullptr);
-  const int Pp = b.Pp;
-  typedef const __nv_bfloat16* CB;
-  pe_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(P, Pp, x, t, n.has_timenet, n.has_timenet ? 6 : 10, b.A5, b.T0,
-                                             train ? b.A5T : nullptr, train ? b.T0T : nullptr);
+  const int Pp = b.Pp, tiles = b.tiles;
+  pe_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(P, Pp, x, t, n.has_timenet, n.has_timenet ? 6 : 10, b.A5, b.T0);
   if (n.has_timenet) {
-    GemmArgs g = gemm(b.T0, 16, (CB)n.Wt0, 16, Pp, WID, 16);
-    g.bias = n.bt0; g.relu = 1; g.out_bf16 = b.T1; g.ld_bf16 = WID; g.out_bf16_t = b.T1T; g.ld_t = Pp;
-    CK(launch_gemm(g, s));
-    g = gemm(b.T1, WID, (CB)n.Wt1, WID, Pp, n.in_t, WID);
-    g.bias = n.bt1; g.out_bf16 = b.A5 + TCOL; g.ld_bf16 = K5;
-    g.out_bf16_t = train ? b.A5T + (size_t)TCOL * Pp : nullptr; g.ld_t = Pp;
-    CK(launch_gemm(g, s));
+    LayerArgs g = layer(BlkView{b.T0, (size_t)16 * ACT_R, 0}, 16, (CB)n.Wt0, WID, tiles);
+    g.bias = n.bt0; g.relu = 1; g.out = b.T1; g.out_tile_stride = (size_t)WID * ACT_R;
+    CK(launch_layer_gemm(g, s));
+    g = layer(BlkView{b.T1, (size_t)WID * ACT_R, 0}, WID, (CB)n.Wt1, 32, tiles);  // 30 outputs padded to 32
+    g.bias = n.bt1; g.out = b.A5; g.out_tile_stride = (size_t)K5 * ACT_R; g.out_kb0 = TCOL / 8;
+    CK(launch_layer_gemm(g, s));
   }
   for (int l = 0; l < 8; ++l) {
-    const __nv_bfloat16* A = (l == 0 || l == 5) ? b.A5 : b.H[l - 1];
-    const int lda = (l == 0 || l == 5) ? K5 : WID, K = (l == 0) ? K0 : (l == 5 ? K5 : WID);
-    GemmArgs g = gemm(A, lda, (CB)n.W[l], K, Pp, WID, K);
+    const BlkView A = (l == 0 || l == 5) ? b.a5() : b.h(l - 1);
+    const int K = (l == 0) ? K0 : (l == 5 ? K5 : WID);
+    LayerArgs g = layer(A, K, (CB)n.W[l], WID, tiles);
     g.bias = n.b[l]; g.relu = 1;
-    g.out_bf16 = b.H[l]; g.ld_bf16 = (l == 4) ? K5 : WID;
-    g.out_bf16_t = b.HT[l]; g.ld_t = Pp;
-    CK(launch_gemm(g, s));
+    const BlkView o = b.h(l);
+    g.out = const_cast<__nv_bfloat16*>(o.p); g.out_tile_stride = o.tile_stride; g.out_kb0 = o.kb0;
+    CK(launch_layer_gemm(g, s));
   }
-  GemmArgs g = gemm(b.H[7], WID, (CB)n.Wh, WID, P, n.n_out, WID);
-  g.bias = n.bh; g.out_f32 = out; g.ld_f32 = 16;
-  CK(launch_gemm(g, s));
+  LayerArgs g = layer(b.h(7), WID, (CB)n.Wh, 16, tiles);
+  g.bias = n.bh; g.out_f32 = out; g.ld_f32 = 16; g.n_f32 = 16; g.rows_valid = P;
+  CK(launch_layer_gemm(g, s));
   if (n.sigmoid_out) sigmoid_kernel<<<(P * 16 + 255) / 256, 256, 0, s>>>(P * 16, out);
   return cudaGetLastError();
 }
 
-// weight gradient: dW[out, Kin] += dZT[out, Pp] . HT[Kin, Pp]^T   (split over the points)
-static cudaError_t dw_gemm(const __nv_bfloat16* dZT, int M, const __nv_bfloat16* HT, int N, int Pp, float* dW, int ldw,
-                           cudaStream_t s) {
-  GemmArgs g = gemm(dZT, Pp, HT, Pp, M, N, Pp);
-  const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
-  int splits = max(1, 296 / tiles);
-  g.k_split = max(64, ((Pp + splits - 1) / splits + 63) / 64 * 64);
-  g.out_f32 = dW; g.ld_f32 = ldw; g.atomic = 1;
-  return launch_gemm(g, s);
+// weight gradient C[256 (X features), N (Y features)] (+)= X^T Y, or its transpose
+static cudaError_t dw(const BlkView& X, const BlkView& Y, int N, int tiles, float* C, int ld, int transpose,
+                      cudaStream_t s) {
+  DwArgs g = {};
+  g.X = X; g.Y = Y; g.N = N; g.tiles = tiles; g.C = C; g.ld = ld; g.transpose = transpose;
+  g.m_valid = WID; g.n_valid = N;
+  return launch_dw_gemm(g, s);
 }
 
 cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const float* out, const float* g_out,
                                 void* ws, const DglGrads& gr, float* dx, cudaStream_t s) {
   MlpBufs b = MlpBufs::carve_all((char*)ws, P, 1, nullptr);
-  const int Pp = b.Pp;
-  typedef const __nv_bfloat16* CB;
-  const int rb = (Pp + COLSUM_ROWS - 1) / COLSUM_ROWS;
+  const int Pp = b.Pp, tiles = b.tiles;
+  const size_t HS = (size_t)WID * ACT_R;  // tile stride of a 256-feature activation
   cudaMemsetAsync(b.dE, 0, sizeof(float) * (size_t)Pp * K0, s);
   for (int l = 0; l < 8; ++l) {
     const int K = (l == 0) ? K0 : (l == 5 ? K5 : WID);
@@ -333,47 +319,53 @@ cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const fl
     cudaMemsetAsync(gr.dWt1, 0, sizeof(float) * 32 * WID, s);
     cudaMemsetAsync(gr.dbt1, 0, sizeof(float) * 32, s);
   }
-  // heads
-  head_grad_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(P, Pp, n.n_out, n.sigmoid_out, g_out, out, b.dZh, b.dZhT);
-  CK(dw_gemm(b.dZhT, 16, b.HT[7], WID, Pp, gr.dWh, WID, s));
-  colsum_kernel<<<rb, 256, 0, s>>>(Pp, 16, 16, b.dZh, gr.dbh);
+  // heads: dWh[16,256] = dZh^T . H7 (computed transposed: X = H7), dbh, dZ7 = (dZh . Wh) * relu'(H7)
+  const BlkView vZh{b.dZh, (size_t)16 * ACT_R, 0};
+  head_grad_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(P, Pp, n.n_out, n.sigmoid_out, g_out, out, b.dZh);
+  CK(dw(b.h(7), vZh, 16, tiles, gr.dWh, WID, 1, s));
+  colsum_blk_kernel<<<tiles, 256, 0, s>>>(16, b.dZh, gr.dbh);
   int cur = 0;
   {
-    GemmArgs g = gemm(b.dZh, 16, (CB)n.WhT, 16, Pp, WID, 16);  // dH7 = dZh . Wh, masked by ReLU'(H7)
-    g.mask = b.H[7]; g.ld_mask = WID;
-    g.out_bf16 = b.dZ[cur]; g.ld_bf16 = WID; g.out_bf16_t = b.dZT[cur]; g.ld_t = Pp;
-    CK(launch_gemm(g, s));
+    LayerArgs g = layer(vZh, 16, (CB)n.WhT, WID, tiles);
+    g.mask = b.h(7);
+    g.out = b.dZ[cur]; g.out_tile_stride = HS;
+    CK(launch_layer_gemm(g, s));
   }
   for (int l = 7; l >= 0; --l) {
     // dZ[cur] = dL/d(pre-activation of layer l)
-    const int K = (l == 0) ? K0 : (l == 5 ? K5 : WID);
-    const __nv_bfloat16* HinT = (l == 0 || l == 5) ? b.A5T : b.HT[l - 1];
-    CK(dw_gemm(b.dZT[cur], WID, HinT, K, Pp, gr.dW[l], K, s));
-    colsum_kernel<<<rb, 256, 0, s>>>(Pp, WID, WID, b.dZ[cur], gr.db[l]);
+    const BlkView vZ{b.dZ[cur], HS, 0};
+    if (l == 0 || l == 5) {
+      CK(dw(vZ, b.a5(), K0, tiles, gr.dW[l], (l == 0) ? K0 : K5, 0, s));            // columns of [x_emb, t]
+      if (l == 5) CK(dw(vZ, b.h(4), WID, tiles, gr.dW[l] + K0, K5, 0, s));          // columns of h4
+    } else {
+      CK(dw(vZ, b.h(l - 1), WID, tiles, gr.dW[l], WID, 0, s));
+    }
+    colsum_blk_kernel<<<tiles, 256, 0, s>>>(WID, b.dZ[cur], gr.db[l]);
     if (l == 0 || l == 5) {  // gradient w.r.t. the embedded inputs (no ReLU in front of them)
-      GemmArgs g = gemm(b.dZ[cur], WID, (CB)n.WT[l], WID, Pp, K0, WID);
-      g.out_f32 = b.dE; g.ld_f32 = K0; g.atomic = 1;
-      CK(launch_gemm(g, s));
+      const CB We = (l == 0) ? (CB)n.WT[0] : (CB)n.WT[5] + (size_t)WID * WID;  // [256/8][96][8]
+      LayerArgs g = layer(vZ, WID, We, K0, tiles);
+      g.out_f32 = b.dE; g.ld_f32 = K0; g.n_f32 = K0; g.atomic = 1; g.rows_valid = Pp;
+      CK(launch_layer_gemm(g, s));
     }
     if (l > 0) {
-      const int off = (l == 5) ? K0 : 0;  // rows of W5^T that belong to h4
-      GemmArgs g = gemm(b.dZ[cur], WID, (CB)n.WT[l] + (size_t)off * WID, WID, Pp, WID, WID);
-      g.mask = b.H[l - 1]; g.ld_mask = (l - 1 == 4) ? K5 : WID;
-      g.out_bf16 = b.dZ[cur ^ 1]; g.ld_bf16 = WID; g.out_bf16_t = b.dZT[cur ^ 1]; g.ld_t = Pp;
-      CK(launch_gemm(g, s));
+      LayerArgs g = layer(vZ, WID, (CB)n.WT[l], WID, tiles);  // for l == 5 the h4 part comes first
+      g.mask = b.h(l - 1);
+      g.out = b.dZ[cur ^ 1]; g.out_tile_stride = HS;
+      CK(launch_layer_gemm(g, s));
       cur ^= 1;
     }
   }
   if (n.has_timenet) {
-    tfeat_grad_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(Pp, n.in_t, b.dE, b.dZt1, b.dZt1T);
-    CK(dw_gemm(b.dZt1T, 32, b.T1T, WID, Pp, gr.dWt1, WID, s));
-    colsum_kernel<<<rb, 256, 0, s>>>(Pp, 32, 32, b.dZt1, gr.dbt1);
-    GemmArgs g = gemm(b.dZt1, 32, (CB)n.Wt1T, 32, Pp, WID, 32);
-    g.mask = b.T1; g.ld_mask = WID;
-    g.out_bf16 = b.dZ[cur ^ 1]; g.ld_bf16 = WID; g.out_bf16_t = b.dZT[cur ^ 1]; g.ld_t = Pp;
-    CK(launch_gemm(g, s));
-    CK(dw_gemm(b.dZT[cur ^ 1], WID, b.T0T, 16, Pp, gr.dWt0, 16, s));
-    colsum_kernel<<<rb, 256, 0, s>>>(Pp, WID, WID, b.dZ[cur ^ 1], gr.dbt0);
+    const BlkView vT1{b.T1, HS, 0}, vZt1{b.dZt1, (size_t)32 * ACT_R, 0};
+    tfeat_grad_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(Pp, n.in_t, b.dE, b.dZt1);
+    CK(dw(vT1, vZt1, 32, tiles, gr.dWt1, WID, 1, s));   // dWt1[32,256] = dZt1^T . T1 (transposed form)
+    colsum_blk_kernel<<<tiles, 256, 0, s>>>(32, b.dZt1, gr.dbt1);
+    LayerArgs g = layer(vZt1, 32, (CB)n.Wt1T, WID, tiles);
+    g.mask = vT1;
+    g.out = b.dZ[cur ^ 1]; g.out_tile_stride = HS;
+    CK(launch_layer_gemm(g, s));
+    CK(dw(BlkView{b.dZ[cur ^ 1], HS, 0}, BlkView{b.T0, (size_t)16 * ACT_R, 0}, 16, tiles, gr.dWt0, 16, 0, s));
+    colsum_blk_kernel<<<tiles, 256, 0, s>>>(WID, b.dZ[cur ^ 1], gr.dbt0);
   }
   if (dx) pe_backward_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, x, b.dE, dx);
   return cudaGetLastError();
@@ -385,11 +377,67 @@ size_t mlp_workspace_bytes(int P, int train) {
   return bytes;
 }
 
+// ------------------------------------------------------------------ stand-alone GEMM entry points (tests)
+// row-major bf16 [rows, ld] (cols valid) -> blocked with R-row tiles and Fp features (zero padded)
+__global__ void rm_to_blk_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int ld, int R, int Fp,
+                                 int rows_pad, __nv_bfloat16* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows_pad * Fp) return;
+  const int row = (int)(i / Fp), f = (int)(i % Fp);
+  const __nv_bfloat16 v = (row < rows && f < cols) ? src[(size_t)row * ld + f] : __float2bfloat16_rn(0.f);
+  dst[(size_t)(row / R) * Fp * R + ((size_t)(f >> 3) * R + row % R) * 8 + (f & 7)] = v;
+}
+
+size_t gemm_test_ws_bytes(int M, int N, int K) {
+  const size_t Mp = ((size_t)M + ACT_R - 1) / ACT_R * ACT_R, Np = ((size_t)N + 15) / 16 * 16,
+               Kp = ((size_t)K + 15) / 16 * 16;
+  return (Mp * Kp + Np * Kp + Mp * 256 + Mp * Np) * 2 + 1024;
+}
+
+// C[M,N] = A[M,K] . B[N,K]^T through layer_gemm_kernel
+cudaError_t launch_gemm_test(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const float* bias,
+                             int relu, float* C, int ldc, void* ws, cudaStream_t s) {
+  const int Mp = (M + ACT_R - 1) / ACT_R * ACT_R, Np = (N + 15) / 16 * 16, Kp = (K + 15) / 16 * 16;
+  char* p = (char*)ws;
+  __nv_bfloat16* Ab = carve<__nv_bfloat16>(p, (size_t)Mp * Kp);
+  __nv_bfloat16* Bb = carve<__nv_bfloat16>(p, (size_t)Np * Kp);
+  rm_to_blk_kernel<<<(unsigned)(((size_t)Mp * Kp + 255) / 256), 256, 0, s>>>((CB)A, M, K, lda, ACT_R, Kp, Mp, Ab);
+  rm_to_blk_kernel<<<(unsigned)(((size_t)Np * Kp + 255) / 256), 256, 0, s>>>((CB)B, N, K, ldb, Np, Kp, Np, Bb);
+  LayerArgs g = layer(BlkView{Ab, (size_t)Kp * ACT_R, 0}, Kp, Bb, Np, Mp / ACT_R);
+  g.bias = bias; g.relu = relu;
+  g.out_f32 = C; g.ld_f32 = ldc; g.n_f32 = N; g.rows_valid = M;
+  // the bias vector has N entries; the kernel reads bias[i] for i < g.N = Np: guard with a padded copy
+  if (bias && Np != N) {
+    float* bp = carve<float>(p, 256);
+    cudaMemsetAsync(bp, 0, 256 * sizeof(float), s);
+    cudaMemcpyAsync(bp, bias, sizeof(float) * N, cudaMemcpyDeviceToDevice, s);
+    g.bias = bp;
+  }
+  return launch_layer_gemm(g, s);
+}
+
+// C[Mf,Nf] (+)= X[P,Mf]^T . Y[P,Nf] through dw_gemm_kernel (Mf <= 256, Nf <= 256)
+cudaError_t launch_gemm_tn_test(int P, int Mf, int Nf, const void* X, int ldx, const void* Y, int ldy, float* C,
+                                int ldc, int transpose, void* ws, cudaStream_t s) {
+  const int Pp = (P + ACT_R - 1) / ACT_R * ACT_R, Np = (Nf + 15) / 16 * 16;
+  char* p = (char*)ws;
+  __nv_bfloat16* Xb = carve<__nv_bfloat16>(p, (size_t)Pp * 256);
+  __nv_bfloat16* Yb = carve<__nv_bfloat16>(p, (size_t)Pp * Np);
+  rm_to_blk_kernel<<<(unsigned)(((size_t)Pp * 256 + 255) / 256), 256, 0, s>>>((CB)X, P, Mf, ldx, ACT_R, 256, Pp, Xb);
+  rm_to_blk_kernel<<<(unsigned)(((size_t)Pp * Np + 255) / 256), 256, 0, s>>>((CB)Y, P, Nf, ldy, ACT_R, Np, Pp, Yb);
+  DwArgs g = {};
+  g.X = BlkView{Xb, (size_t)256 * ACT_R, 0};
+  g.Y = BlkView{Yb, (size_t)Np * ACT_R, 0};
+  g.N = Np; g.tiles = Pp / ACT_R; g.C = C; g.ld = ldc; g.transpose = transpose;
+  g.m_valid = Mf; g.n_valid = transpose ? Nf : (Nf + 3) / 4 * 4;
+  return launch_dw_gemm(g, s);
+}
+
 }  // namespace dgm
 
 // =====================================================================================
-// Parameter packing: reference-shaped fp32 parameters (nn.Linear weights [out, in]) -> the padded
-// bf16 matrices + transposes of DglNet, and packed fp32 gradients -> reference-shaped gradients.
+// Parameter packing: reference-shaped fp32 parameters (nn.Linear weights [out, in]) -> the blocked
+// bf16 operands of DglNet, and packed fp32 gradients -> reference-shaped gradients.
 // Column map of an input-facing matrix: c < 63 -> c ; 63 <= c < 63+in_t -> c + 1 ; beyond (the
 // hidden part of the skip layer) -> 96 + (c - 63 - in_t).
 // =====================================================================================
@@ -402,16 +450,30 @@ __device__ __forceinline__ int map_col(int c, int in_t, int mapped) {
   return K0 + (c - XE - in_t);
 }
 
-// src fp32 [rows, kin] -> dst bf16 [rows_pad?, kpad] at row offset r0 (+ transposed [kpad, ldt])
-__global__ void pack_w_kernel(const float* __restrict__ src, int rows, int kin, int in_t, int mapped, int r0,
-                              __nv_bfloat16* __restrict__ dst, int kpad, __nv_bfloat16* __restrict__ dstT, int ldt) {
+// src fp32 [rows, kin] (nn.Linear layout [out, in]) -> blocked bf16 operands (mlp_gemm.cuh):
+//   forward  B operand  dst : single tile of Rf rows (outputs), element (o, k) at ((k/8)*Rf + o)*8 + k%8
+//   backward B operand  dstT: rows = inputs j, contraction index = outputs o:
+//            element (j, o) at ((o/8)*Rt + j)*8 + o%8.  For the input-facing layers the input columns
+//            split into the [x_emb, t] block (j < 96, Rt = 96, at dstT_e) and the hidden block
+//            (j >= 96 -> j - 96, Rt = 256, at dstT).
+__global__ void pack_w_kernel(const float* __restrict__ src, int rows, int kin, int in_t, int mapped, int r0, int Rf,
+                              __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dstT, int Rt,
+                              __nv_bfloat16* __restrict__ dstT_e) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * kin) return;
   const int r = i / kin, c = i % kin;
-  const int cc = map_col(c, in_t, mapped);
+  const int cc = map_col(c, in_t, mapped), o = r0 + r;
   const __nv_bfloat16 v = __float2bfloat16_rn(src[i]);
-  dst[(size_t)(r0 + r) * kpad + cc] = v;
-  if (dstT) dstT[(size_t)cc * ldt + r0 + r] = v;
+  dst[((size_t)(cc >> 3) * Rf + o) * 8 + (cc & 7)] = v;
+  if (mapped) {
+    if (cc < K0) {
+      if (dstT_e) dstT_e[((size_t)(o >> 3) * K0 + cc) * 8 + (o & 7)] = v;
+    } else if (dstT) {
+      dstT[((size_t)(o >> 3) * WID + (cc - K0)) * 8 + (o & 7)] = v;
+    }
+  } else if (dstT) {
+    dstT[((size_t)(o >> 3) * Rt + cc) * 8 + (o & 7)] = v;
+  }
 }
 // packed fp32 grad [*, kpad] (row offset r0) -> reference-shaped [rows, kin]
 __global__ void unpack_w_kernel(const float* __restrict__ src, int kpad, int r0, int rows, int kin, int in_t,
@@ -478,30 +540,34 @@ cudaError_t launch_mlp_pack(const DglRaw& r, void* wbuf, float* bbuf, DglNet* ne
   cudaMemsetAsync(wbuf, 0, L.w_total * 2, s);
   cudaMemsetAsync(bbuf, 0, L.b_total * 4, s);
   net->has_timenet = r.has_timenet; net->in_t = r.in_t; net->sigmoid_out = r.sigmoid_out;
-  auto pack = [&](const float* src, int rows, int kin, int mapped, int r0, size_t dst, int kpad, size_t dstT,
-                  int ldt) {
+  const size_t NONE = (size_t)-1;
+  auto at = [&](size_t off) { return off == NONE ? (__nv_bfloat16*)nullptr : w + off; };
+  auto pack = [&](const float* src, int rows, int kin, int mapped, int r0, int Rf, size_t dst, size_t dstT, int Rt,
+                  size_t dstT_e) {
     const int n = rows * kin;
-    pack_w_kernel<<<(n + 255) / 256, 256, 0, s>>>(src, rows, kin, r.in_t, mapped, r0, w + dst, kpad,
-                                                  dstT != (size_t)-1 ? w + dstT : nullptr, ldt);
+    pack_w_kernel<<<(n + 255) / 256, 256, 0, s>>>(src, rows, kin, r.in_t, mapped, r0, Rf, w + dst, at(dstT), Rt,
+                                                  at(dstT_e));
   };
   for (int l = 0; l < 8; ++l) {
     const int kin = (l == 0) ? in_width(r) : (l == 5 ? in_width(r) + WID : WID);
-    const int kpad = (l == 0) ? K0 : (l == 5 ? K5 : WID);
-    pack(r.W[l], WID, kin, l == 0 || l == 5, 0, L.W[l], kpad, L.WT[l], WID);
+    // WT[0] holds only the [x_emb, t] block; WT[5] the hidden block followed by the [x_emb, t] block
+    if (l == 0) pack(r.W[l], WID, kin, 1, 0, WID, L.W[l], NONE, 0, L.WT[l]);
+    else if (l == 5) pack(r.W[l], WID, kin, 1, 0, WID, L.W[l], L.WT[l], WID, L.WT[l] + (size_t)WID * WID);
+    else pack(r.W[l], WID, kin, 0, 0, WID, L.W[l], L.WT[l], WID, NONE);
     copy_f32_kernel<<<1, 256, 0, s>>>(r.b[l], WID, bbuf + L.b[l]);
     net->W[l] = w + L.W[l]; net->WT[l] = w + L.WT[l]; net->b[l] = bbuf + L.b[l];
   }
   int r0 = 0;
   for (int h = 0; h < r.n_heads; ++h) {
-    pack(r.Wh[h], r.head_rows[h], WID, 0, r0, L.Wh, WID, L.WhT, 16);
+    pack(r.Wh[h], r.head_rows[h], WID, 0, r0, 16, L.Wh, L.WhT, WID, NONE);
     copy_f32_kernel<<<1, 256, 0, s>>>(r.bh[h], r.head_rows[h], bbuf + L.bh + r0);
     r0 += r.head_rows[h];
   }
   net->n_out = r0;
   net->Wh = w + L.Wh; net->WhT = w + L.WhT; net->bh = bbuf + L.bh;
   if (r.has_timenet) {
-    pack(r.Wt0, WID, 13, 0, 0, L.Wt0, 16, (size_t)-1, 0);
-    pack(r.Wt1, r.in_t, WID, 0, 0, L.Wt1, WID, L.Wt1T, 32);
+    pack(r.Wt0, WID, 13, 0, 0, WID, L.Wt0, NONE, 0, NONE);
+    pack(r.Wt1, r.in_t, WID, 0, 0, 32, L.Wt1, L.Wt1T, WID, NONE);
     copy_f32_kernel<<<1, 256, 0, s>>>(r.bt0, WID, bbuf + L.bt0);
     copy_f32_kernel<<<1, 256, 0, s>>>(r.bt1, r.in_t, bbuf + L.bt1);
     net->Wt0 = w + L.Wt0; net->Wt1 = w + L.Wt1; net->Wt1T = w + L.Wt1T;

@@ -1,193 +1,322 @@
-// mlp_gemm.cuh -- bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulator in
-// TMEM), the building block of the deformation / appearance MLPs.
+// mlp_gemm.cuh -- the two tensor-core kernels of the deformation / appearance MLPs (tcgen05.mma, bf16
+// operands, fp32 accumulators in TMEM), built around ONE global data layout.
 //
-//   D[M,N] = A[M,K] * B[N,K]^T          A, B row-major bf16 (K contiguous), fp32 accumulate
+// Blocked ("K-blocked") bf16 layout.  A matrix with F feature columns (F % 8 == 0) is stored in row
+// tiles of R rows:  element (row, f) lives at
+//     tile(row / R) * tile_stride  +  ((f / 8) * R + row % R) * 8 + f % 8            [elements]
+// i.e. per tile, per 8-feature block ("kb"), R units of 16 bytes.  Activations use R = 128 (one tile =
+// one 128-point M tile), weight matrices a single tile with R = number of output rows.
+// Why: (1) a K-chunk of a tile (8 kbs) is ONE contiguous piece of memory that is already in the UMMA
+// no-swizzle core-matrix order, so an operand stage is filled by a single 1-D bulk copy
+// (cp.async.bulk + mbarrier complete_tx) issued by one thread -- no per-thread address arithmetic,
+// no tensor maps; (2) the epilogue's stores are fully coalesced (32 lanes = 32 consecutive rows = 512
+// contiguous bytes per instruction); (3) the SAME stored activations serve as MN-major operands of
+// the weight-gradient GEMM (contraction over the points), so no transposed copies are ever written.
 //
-// One CTA (4 warps) owns a 128 x BN output tile: operands are staged global -> shared with 16-byte
-// cp.async copies straight into the UMMA core-matrix layout (umma.cuh), 2-stage ring; ONE thread
-// issues the tcgen05.mma instructions (M=128, N=BN, K=16) and commits each stage to an mbarrier;
-// after the last commit the four warps read their 32 TMEM lanes (tcgen05.ld 32x32b.x32) and run the
-// fused epilogue: + bias, ReLU, ReLU-mask (for dZ = dA * [act > 0]), then any of: fp32 store,
-// fp32 split-K reduction (red.global.add.v4), bf16 store, transposed bf16 store.
+//   layer_gemm_kernel   D[rows, N] = A[rows, K] . B[N, K]^T          (forward layers, dZ back-propagation)
+//       persistent CTAs (one per SM) over the 128-row tiles; warp-specialised:
+//         warp 0    producer: per K-chunk one bulk copy for A and one for B into a 4-stage ring
+//         warp 1    issues tcgen05.mma (M = 128, N <= 256, K = 16) into one of TWO TMEM accumulators
+//         warps 2-5 epilogue of the previous tile (tcgen05.ld -> bias / ReLU / ReLU-mask -> blocked
+//                   bf16 store, fp32 store or fp32 reduction) while the next tile is being multiplied
+//   dw_gemm_kernel      C[Mf, Nf] += X[rows, Mf]^T . Y[rows, Nf]     (weight gradients)
+//       both operands MN-major straight from the blocked activations; each CTA accumulates its share
+//       of the row tiles in TMEM and adds its partial result to C once (red.global.add).
 #pragma once
 #include "umma.cuh"
 
 namespace dgm {
 
-struct GemmArgs {
-  const __nv_bfloat16* A;
-  const __nv_bfloat16* B;
-  int lda, ldb;        // elements, multiples of 8
-  int M, N, K;         // K multiple of 8
-  int k_split;         // K elements per blockIdx.z slice (multiple of 64), == K when not split
-  const float* bias;   // [N] or null
-  int relu;            // apply max(0, .)
-  const __nv_bfloat16* mask;  // [M, ld_mask] or null: multiply by (mask > 0)
-  int ld_mask;
-  float* out_f32;      // [M, ld_f32] or null
-  int ld_f32;
-  int atomic;          // accumulate into out_f32 with reductions (split-K)
-  __nv_bfloat16* out_bf16;    // [M, ld_bf16] or null
-  int ld_bf16;
-  __nv_bfloat16* out_bf16_t;  // [N, ld_t] or null (transposed copy)
-  int ld_t;
+#define ACT_R 128             // rows per activation tile
+#define KB_ELEMS (ACT_R * 8)  // elements of one 8-feature block of an activation tile (2 KB)
+
+// view of a blocked activation matrix: pointer to tile 0, elements between tiles, first kb used
+struct BlkView {
+  const __nv_bfloat16* p;
+  size_t tile_stride;
+  int kb0;
 };
 
-#define GEMM_BM 128
-#define GEMM_BK 64
-#define GEMM_STAGES 2  // 2 x (16 + 32) KB at BN = 256: two CTAs per SM, one's epilogue overlaps the other's main loop
+struct LayerArgs {
+  BlkView A;                  // [tiles*128, K]
+  const __nv_bfloat16* B;     // blocked single tile, R = N rows: [K/8][N][8]
+  int K, N;                   // K % 16 == 0, N % 16 == 0, 16 <= N <= 256
+  int tiles;                  // 128-row tiles
+  int rows_valid;             // rows < rows_valid are written to the fp32 output
+  const float* bias;          // [N] or null
+  int relu;
+  BlkView mask;               // p == null: none; else keep where mask > 0 (same rows, N columns from mask.kb0)
+  __nv_bfloat16* out;         // blocked output (N columns from out_kb0) or null
+  size_t out_tile_stride;
+  int out_kb0;
+  float* out_f32;             // row-major [rows, ld_f32] or null; first n_f32 columns
+  int ld_f32, n_f32, atomic;  // atomic: accumulate with red.global.add
+};
 
-template <int BN>
-__global__ void __launch_bounds__(128) gemm_tn_kernel(const GemmArgs g) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB per stage
-  constexpr int B_BYTES = BN * GEMM_BK * 2;
-  constexpr int LBO_A = GEMM_BM * 16, LBO_B = BN * 16;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  __shared__ __align__(8) uint64_t s_bar[GEMM_STAGES];
+#define LG_STAGES 4
+#define LG_A_BYTES (ACT_R * 64 * 2)  // 16 KB: 128 rows x 64 K
+#define LG_B_BYTES (256 * 64 * 2)    // 32 KB: up to 256 rows x 64 K
+#define LG_THREADS 192
+#define LG_SMEM (LG_STAGES * (LG_A_BYTES + LG_B_BYTES) + 1024)
+
+__global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[LG_STAGES], s_empty[LG_STAGES], s_acc_full[2], s_acc_empty[2];
   __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
-  const int kbeg = blockIdx.z * g.k_split, kend = min(g.K, kbeg + g.k_split);
-  const int nk = (kend - kbeg + GEMM_BK - 1) / GEMM_BK;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 1 KB aligned operand ring
+  const uint32_t sA = ring, sB = ring + LG_STAGES * LG_A_BYTES;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < GEMM_STAGES; ++s) mbar_init(&s_bar[s], 1);
+    for (int s = 0; s < LG_STAGES; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 1);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_acc_full[b], 1);
+      mbar_init(&s_acc_empty[b], 128);
+    }
     mbar_fence_init();
   }
-  if (warp == 0) umma::tmem_alloc(&s_tmem, TMEM_COLS);
+  for (int i = tid; i < 256; i += LG_THREADS) s_bias[i] = (g.bias && i < g.N) ? g.bias[i] : 0.f;
+  if (warp == 1) umma::tmem_alloc(&s_tmem, 512);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = s_tmem;
-  const uint32_t sA = smem_u32(smem), sB = sA + GEMM_STAGES * A_BYTES;
 
-  auto load_chunk = [&](int c) {
-    const int st = c % GEMM_STAGES;
-    const int k0 = kbeg + c * GEMM_BK;
-    // A: 128 rows x 8 k-blocks.  A warp-iteration covers 8 rows x 4 k-blocks (64 B per row from
-    // global, 4 shared-memory wavefronts -- the minimum for 512 B).
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int w = it * 4 + warp;
-      const int row = (w >> 1) * 8 + (lane & 7), kb = (w & 1) * 4 + (lane >> 3);
-      const int gr = m0 + row, gk = k0 + kb * 8;
-      const bool ok = gr < g.M && gk < kend;
-      const __nv_bfloat16* src = ok ? g.A + (size_t)gr * g.lda + gk : g.A;
-      umma::cp_async16(sA + st * A_BYTES + kb * LBO_A + (row >> 3) * 128 + (row & 7) * 16, src, ok ? 16u : 0u);
-    }
-#pragma unroll
-    for (int it = 0; it < BN / 16; ++it) {
-      const int w = it * 4 + warp;
-      const int row = (w >> 1) * 8 + (lane & 7), kb = (w & 1) * 4 + (lane >> 3);
-      const int gr = n0 + row, gk = k0 + kb * 8;
-      const bool ok = gr < g.N && gk < kend;
-      const __nv_bfloat16* src = ok ? g.B + (size_t)gr * g.ldb + gk : g.B;
-      umma::cp_async16(sB + st * B_BYTES + kb * LBO_B + (row >> 3) * 128 + (row & 7) * 16, src, ok ? 16u : 0u);
-    }
-  };
+  const int nkb = g.K >> 3;            // 8-wide k blocks
+  const int nchunks = (nkb + 7) >> 3;  // K chunks of (up to) 64
+  const int my_tiles = (g.tiles > (int)blockIdx.x) ? (g.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  constexpr uint32_t IDESC = umma::instr_desc_bf16(GEMM_BM, BN < 16 ? 16 : BN);
-  // prologue: chunks 0 .. STAGES-2 in flight (one commit group per chunk, empty groups keep the count uniform)
-#pragma unroll
-  for (int c = 0; c < GEMM_STAGES - 1; ++c) {
-    if (c < nk) load_chunk(c);
-    umma::cp_async_commit();
-  }
-  for (int c = 0; c < nk; ++c) {
-    const int cn = c + GEMM_STAGES - 1;  // chunk to prefetch; its stage was last read by the MMAs of chunk c-1
-    if (cn < nk) {
-      if (c >= 1) mbar_wait(&s_bar[(c - 1) % GEMM_STAGES], ((c - 1) / GEMM_STAGES) & 1);
-      load_chunk(cn);
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const __nv_bfloat16* a_tile = g.A.p + (size_t)tile * g.A.tile_stride + (size_t)g.A.kb0 * KB_ELEMS;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int st = it % LG_STAGES;
+          const int kbs = min(8, nkb - 8 * c);
+          mbar_wait(&s_empty[st], ((it / LG_STAGES) & 1) ^ 1);
+          const uint32_t a_bytes = kbs * (ACT_R * 16), b_bytes = kbs * g.N * 16;
+          mbar_expect_tx(&s_full[st], a_bytes + b_bytes);
+          tma_load_1d_u32(sA + st * LG_A_BYTES, a_tile + (size_t)c * 8 * KB_ELEMS, a_bytes, &s_full[st]);
+          tma_load_1d_u32(sB + st * LG_B_BYTES, g.B + (size_t)c * 8 * g.N * 8, b_bytes, &s_full[st]);
+        }
+      }
     }
-    umma::cp_async_commit();
-    umma::cp_async_wait<GEMM_STAGES - 1>();  // chunk c has landed (at most STAGES-1 younger groups in flight)
-    umma::fence_smem_to_async();
-    __syncthreads();
-    if (tid == 0) {
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma::instr_desc_bf16(128, g.N);
+      const uint32_t lbo_b = g.N * 16;
+      uint32_t it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int buf = i & 1;
+        mbar_wait(&s_acc_empty[buf], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        umma::fence_after_sync();
+        const uint32_t d_tmem = tmem + buf * 256;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int st = it % LG_STAGES;
+          const int kbs = min(8, nkb - 8 * c);
+          mbar_wait(&s_full[st], (it / LG_STAGES) & 1);
+          umma::fence_after_sync();
+          for (int ks = 0; ks < (kbs >> 1); ++ks) {
+            const uint64_t da = umma::smem_desc(sA + st * LG_A_BYTES + ks * 2 * (ACT_R * 16), ACT_R * 16, 128);
+            const uint64_t db = umma::smem_desc(sB + st * LG_B_BYTES + ks * 2 * lbo_b, lbo_b, 128);
+            umma::mma_bf16(d_tmem, da, db, idesc, (c | ks) != 0);
+          }
+          umma::commit(&s_empty[st]);  // the stage is reusable once these MMAs have read it
+        }
+        umma::commit(&s_acc_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int lg = warp & 3;       // TMEM lane group this warp may access
+    const int r = lg * 32 + lane;  // row inside the tile
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int buf = i & 1;
+      mbar_wait(&s_acc_full[buf], (i >> 1) & 1);
       umma::fence_after_sync();
-      const int st = c % GEMM_STAGES;
+      const size_t row = (size_t)tile * ACT_R + r;
+#pragma unroll 1
+      for (int c0 = 0; c0 < g.N; c0 += 32) {
+        uint32_t raw[32];
+        umma::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 256 + c0), raw);
+        float v[32];
 #pragma unroll
-      for (int ks = 0; ks < GEMM_BK / 16; ++ks) {
-        const uint64_t da = umma::smem_desc(sA + st * A_BYTES + ks * 2 * LBO_A, LBO_A, 128);
-        const uint64_t db = umma::smem_desc(sB + st * B_BYTES + ks * 2 * LBO_B, LBO_B, 128);
-        umma::mma_bf16(tmem, da, db, IDESC, (c | ks) != 0);
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(raw[j]) + s_bias[c0 + j];
+          if (g.relu) x = fmaxf(x, 0.0f);
+          v[j] = x;
+        }
+        const int nunits = min(4, (g.N - c0) >> 3);  // 8-column units of this 32-column slice
+        if (g.mask.p) {
+          const __nv_bfloat16* mt = g.mask.p + (size_t)tile * g.mask.tile_stride;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (u < nunits) {
+              const uint4 mm =
+                  *reinterpret_cast<const uint4*>(mt + ((size_t)(g.mask.kb0 + (c0 >> 3) + u) * ACT_R + r) * 8);
+              const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mm);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[8 * u + q] = (__bfloat162float(mb[q]) > 0.0f) ? v[8 * u + q] : 0.0f;
+            }
+          }
+        }
+        if (g.out) {
+          __nv_bfloat16* ot = g.out + (size_t)tile * g.out_tile_stride;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (u < nunits) {
+              uint4 pk;
+              __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) p2[q] = __floats2bfloat162_rn(v[8 * u + 2 * q], v[8 * u + 2 * q + 1]);
+              *reinterpret_cast<uint4*>(ot + ((size_t)(g.out_kb0 + (c0 >> 3) + u) * ACT_R + r) * 8) = pk;
+            }
+          }
+        }
+        if (g.out_f32 && row < (size_t)g.rows_valid) {
+          float* dst = g.out_f32 + row * g.ld_f32 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c0 + j < g.n_f32) {
+              if (g.atomic) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+              else *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+        }
       }
-      umma::commit(&s_bar[st]);
+      umma::fence_before_sync();
+      mbar_arrive(&s_acc_empty[buf]);
     }
   }
-  // ---- epilogue: wait for the last commit (it covers every earlier MMA)
-  if (nk > 0) mbar_wait(&s_bar[(nk - 1) % GEMM_STAGES], ((nk - 1) / GEMM_STAGES) & 1);
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    umma::fence_after_sync();
+    umma::tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct DwArgs {
+  BlkView X;      // rows x 256 features: CTA (blockIdx.y) takes features [X.kb0*8 + 128*blockIdx.y, +128)
+  BlkView Y;      // rows x N features from Y.kb0
+  int N;          // multiple of 16, <= 256
+  int tiles;
+  float* C;       // fp32, leading dimension ld
+  int ld;
+  int transpose;  // 0: C[m, n] (m = X feature, n = Y feature);  1: C[n, m]
+  int m_valid;    // X features >= m_valid are not written
+  int n_valid;
+};
+
+#define DW_STAGES 2
+#define DW_A_BYTES (128 * ACT_R * 2)  // 32 KB: 128 features x 128 rows
+#define DW_B_BYTES (256 * ACT_R * 2)  // 64 KB
+#define DW_THREADS 192
+#define DW_SMEM (DW_STAGES * (DW_A_BYTES + DW_B_BYTES) + 1024)
+
+__global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const DwArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[DW_STAGES], s_empty[DW_STAGES], s_acc_full;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = ring, sB = ring + DW_STAGES * DW_A_BYTES;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < DW_STAGES; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 1);
+    }
+    mbar_init(&s_acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) umma::tmem_alloc(&s_tmem, 256);
+  umma::fence_before_sync();
+  __syncthreads();
   umma::fence_after_sync();
-  const int row = m0 + warp * 32 + lane;
-  const bool row_ok = row < g.M;
+  const uint32_t tmem = s_tmem;
+  const int my_tiles = (g.tiles > (int)blockIdx.x) ? (g.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int m0 = blockIdx.y * 128;  // first X feature of this CTA
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int st = i % DW_STAGES;
+        mbar_wait(&s_empty[st], ((i / DW_STAGES) & 1) ^ 1);
+        const uint32_t a_bytes = 16 * (ACT_R * 16), b_bytes = (g.N >> 3) * (ACT_R * 16);
+        mbar_expect_tx(&s_full[st], a_bytes + b_bytes);
+        tma_load_1d_u32(sA + st * DW_A_BYTES,
+                        g.X.p + (size_t)tile * g.X.tile_stride + (size_t)(g.X.kb0 + (m0 >> 3)) * KB_ELEMS, a_bytes,
+                        &s_full[st]);
+        tma_load_1d_u32(sB + st * DW_B_BYTES, g.Y.p + (size_t)tile * g.Y.tile_stride + (size_t)g.Y.kb0 * KB_ELEMS,
+                        b_bytes, &s_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // both operands MN-major: core matrix = 8 rows (K) x 8 features; K groups 128 B apart (LBO),
+      // feature groups one kb = 2 KB apart (SBO)
+      const uint32_t idesc = umma::instr_desc_bf16(128, g.N, 1, 1);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int st = i % DW_STAGES;
+        mbar_wait(&s_full[st], (i / DW_STAGES) & 1);
+        umma::fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < ACT_R / 16; ++ks) {
+          const uint64_t da = umma::smem_desc(sA + st * DW_A_BYTES + ks * 256, 128, ACT_R * 16);
+          const uint64_t db = umma::smem_desc(sB + st * DW_B_BYTES + ks * 256, 128, ACT_R * 16);
+          umma::mma_bf16(tmem, da, db, idesc, (i | ks) != 0);
+        }
+        umma::commit(&s_empty[st]);
+      }
+      if (my_tiles > 0) umma::commit(&s_acc_full);
+    }
+  } else if (my_tiles > 0) {
+    const int lg = warp & 3;
+    const int m = m0 + lg * 32 + lane;  // X feature = accumulator row
+    mbar_wait(&s_acc_full, 0);
+    umma::fence_after_sync();
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    if (n0 + c0 >= g.N) break;  // uniform
-    uint32_t r[32];
-    if (nk > 0) {
-      umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-    } else {
+    for (int c0 = 0; c0 < g.N; c0 += 32) {
+      uint32_t raw[32];
+      umma::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, raw);
+      if (m < g.m_valid) {
+        if (!g.transpose) {
+          float* dst = g.C + (size_t)m * g.ld + c0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) r[i] = 0u;
-    }
-    float v[32];
+          for (int j = 0; j < 32; j += 4)
+            if (c0 + j < g.n_valid)
+              red_add_v4(dst + j, __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]),
+                         __uint_as_float(raw[j + 3]));
+        } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int n = n0 + c0 + i;
-      float x = __uint_as_float(r[i]);
-      if (g.bias && n < g.N) x += g.bias[n];
-      if (g.relu) x = fmaxf(x, 0.0f);
-      v[i] = x;
-    }
-    if (g.mask && row_ok) {
-      const __nv_bfloat16* mrow = g.mask + (size_t)row * g.ld_mask + n0 + c0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (n0 + c0 + i < g.N) {
-          const uint4 mm = *reinterpret_cast<const uint4*>(mrow + i);
-          const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mm);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[i + q] = (__bfloat162float(mb[q]) > 0.0f) ? v[i + q] : 0.0f;
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < g.n_valid) atomicAdd(g.C + (size_t)(c0 + j) * g.ld + m, __uint_as_float(raw[j]));
         }
-      }
-    }
-    if (g.out_f32 && row_ok) {
-      float* dst = g.out_f32 + (size_t)row * g.ld_f32 + n0 + c0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        if (n0 + c0 + i < g.N) {
-          if (g.atomic) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-          else *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-      }
-    }
-    if (g.out_bf16 && row_ok) {
-      __nv_bfloat16* dst = g.out_bf16 + (size_t)row * g.ld_bf16 + n0 + c0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (n0 + c0 + i < g.N) {
-          uint4 pk;
-          __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) p2[q] = __floats2bfloat162_rn(v[i + 2 * q], v[i + 2 * q + 1]);
-          *reinterpret_cast<uint4*>(dst + i) = pk;
-        }
-      }
-    }
-    if (g.out_bf16_t && row_ok) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int n = n0 + c0 + i;
-        if (n < g.N) g.out_bf16_t[(size_t)n * g.ld_t + row] = __float2bfloat16_rn(v[i]);
       }
     }
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 1) {
+    umma::fence_after_sync();
+    umma::tmem_dealloc(tmem, 256);
+  }
 }
 
 }  // namespace dgm

@@ -7,8 +7,11 @@
 #include "../../include/dgmesh_b200.h"
 
 namespace dgm {
-struct GemmArgs;
-cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t s);
+size_t gemm_test_ws_bytes(int M, int N, int K);
+cudaError_t launch_gemm_test(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const float* bias,
+                             int relu, float* C, int ldc, void* ws, cudaStream_t s);
+cudaError_t launch_gemm_tn_test(int P, int Mf, int Nf, const void* X, int ldx, const void* Y, int ldy, float* C,
+                                int ldc, int transpose, void* ws, cudaStream_t s);
 cudaError_t launch_mlp_forward(const DglNet& n, int P, const float* x, const float* t, float* out, int train,
                                void* ws, cudaStream_t s);
 cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const float* out, const float* g_out,

@@ -6,6 +6,9 @@
 // i.e. 8x8 "core matrices" of 128 contiguous bytes, all core matrices of one 8-wide k-block
 // contiguous.  Descriptor: SBO (stride between 8-row groups) = 128 B, LBO (stride between the two
 // k-blocks of one K=16 instruction) = R*16 B.  Field layout per cute/arch/mma_sm100_desc.hpp.
+// The same bytes read as an MN-major operand (rows = the contraction index): core matrix = 8 rows
+// (K) x 8 elements (M/N); LBO = stride between 8-row K groups = 128 B, SBO = stride between
+// 8-element M/N groups = R*16 B (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>).
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -25,12 +28,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
-// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major
-__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
   return (1u << 4)                 // c_format  = F32
          | (1u << 7)               // a_format  = BF16
          | (1u << 10)              // b_format  = BF16
-         | (0u << 15) | (0u << 16) // a_major = b_major = K
+         | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)  // 0 = K-major, 1 = MN-major
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

@@ -226,14 +226,21 @@ int dgmc_backward(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
                   const float* dL_dverts, float* dL_dphi, void* stream);
 
 /* ------------------------------------------------------------------------
- * Tensor-core GEMM building block of the MLPs (tcgen05.mma, fp32 accumulation in TMEM):
- *   C[M,N] (fp32, ldc) = A[M,K] (bf16, lda) * B[N,K]^T (bf16, ldb)  [+ bias[N]] [ReLU]
- * lda, ldb, K multiples of 8; ldc multiple of 4.  Exposed for the parity tests of the
- * building block (torch.matmul on the same bf16 operands is the oracle); the networks below
- * drive the same kernel from inside the library.
+ * Tensor-core GEMM building blocks of the MLPs (tcgen05.mma, bf16 operands, fp32 accumulation in
+ * TMEM), exposed stand-alone for the parity tests (torch.matmul on the same bf16 operands is the
+ * oracle).  The networks below drive the same two kernels on activations kept in the library's
+ * blocked layout; these entry points first copy the row-major operands into that layout inside
+ * `ws` (dgl_gemm_ws_bytes(M, N, K), with M = the long dimension).
+ *   dgl_gemm_bf16   : C[M,N] (fp32, ldc) = A[M,K] (bf16, lda) * B[N,K]^T (bf16, ldb) [+ bias[N]] [ReLU]
+ *                     N <= 256; writes columns [0, N rounded up to 4)         (layer kernel)
+ *   dgl_gemm_tn_bf16: C[Mf,Nf] += X[P,Mf]^T * Y[P,Nf]   (or C[Nf,Mf] when transpose_out); Mf, Nf <= 256;
+ *                     accumulates into C with fp32 reductions                 (weight-gradient kernel)
  * ------------------------------------------------------------------------ */
+int dgl_gemm_ws_bytes(int M, int N, int K, size_t* bytes);
 int dgl_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int ldb,
-                  const float* bias, int relu, float* C, int ldc, int k_split, void* stream);
+                  const float* bias, int relu, float* C, int ldc, void* ws, size_t ws_bytes, void* stream);
+int dgl_gemm_tn_bf16(int P, int Mf, int Nf, const void* X, int ldx, const void* Y, int ldy, float* C, int ldc,
+                     int transpose_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Deformation / appearance MLPs (dgmesh/utils/time_utils.py:58-323: DeformNetwork,
@@ -242,10 +249,11 @@ int dgl_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, in
  * The reference runs ~30 fp32 cuBLAS / elementwise kernels per call; here the whole network is a
  * chain of bf16 tcgen05 GEMMs (fp32 accumulation) with fused bias / ReLU epilogues.
  *
- * DglNet describes one network with PACKED parameters (built by the host mirror, see
- * dg-mesh_b200/utils/time_utils.py): bf16 row-major weights [out, Kpad] and their transposes
- * [Kpad, out]; fp32 biases.  Input columns: 0..62 pe(x,10) | 63 zero | 64.. time features | zero
- * pad to 96; the skip layer (index 5) sees those 96 columns followed by the 256 hidden units.
+ * DglNet describes one network with PACKED parameters (built by dgl_mlp_pack): bf16 weights in the
+ * blocked operand layout of the GEMM kernels (dg-mesh_b200/csrc/mlp_gemm.cuh: element (row, k) of
+ * an R-row matrix at ((k/8)*R + row)*8 + k%8) and fp32 biases.  Input columns: 0..62 pe(x,10) |
+ * 63 zero | 64.. time features | zero pad to 96; the skip layer (index 5) sees those 96 columns
+ * followed by the 256 hidden units.
  *   x[P,3], t[P] fp32  ->  out[P,16] fp32 (first n_out columns valid; column order = the
  *   reference's heads concatenated: warp 3, rotation 4, scaling 3, normal 3 / colour 3)
  * train != 0 additionally stores what dgl_mlp_backward needs in the workspace.
@@ -257,16 +265,17 @@ typedef struct DglNet {
   int in_t;          /* 30 or 21 */
   int n_out;         /* <= 16 */
   int sigmoid_out;   /* AppearanceNetwork */
-  const void* W[8];  /* bf16 [256, Kpad_l], Kpad = 96, 256 x4, 352, 256 x2 */
-  const void* WT[8]; /* bf16 [Kpad_l, 256] */
+  const void* W[8];  /* forward operand: 256 rows (outputs) x Kpad_l, Kpad = 96, 256 x4, 352, 256 x2 */
+  const void* WT[8]; /* backward operand: rows = inputs, K = the 256 outputs.  WT[0]: the 96 [x_emb,t]
+                        rows only; WT[5]: the 256 hidden rows, then (at +65536 elements) the 96 rows */
   const float* b[8];
-  const void* Wh;    /* bf16 [16, 256] */
-  const void* WhT;   /* bf16 [256, 16] */
+  const void* Wh;    /* 16 rows x 256 */
+  const void* WhT;   /* 256 rows x 16 */
   const float* bh;   /* [16] */
-  const void* Wt0;   /* bf16 [256, 16]   timenet.0 (13 -> 256), input padded to 16 */
+  const void* Wt0;   /* 256 rows x 16    timenet.0 (13 -> 256), input padded to 16 */
   const float* bt0;
-  const void* Wt1;   /* bf16 [32, 256]   timenet.2 (256 -> 30), output padded to 32 */
-  const void* Wt1T;  /* bf16 [256, 32] */
+  const void* Wt1;   /* 32 rows x 256    timenet.2 (256 -> 30), output padded to 32 */
+  const void* Wt1T;  /* 256 rows x 32 */
   const float* bt1;  /* [32] */
 } DglNet;
 

@@ -62,6 +62,7 @@ cudaError_t launch_dw_gemm(const DwArgs& g, cudaStream_t s) {
 struct MlpBufs {
   __nv_bfloat16 *A5, *T0, *T1, *H[8];  // H[4] = A5 viewed from kb 12
   __nv_bfloat16 *dZ[2], *dZh, *dZt1;
+  uint32_t *M[8], *Mt1;                 // ReLU masks as bits, [tiles][8][128] words (training only)
   float* dE;                            // [Pp, 96] fp32 row-major: gradient w.r.t. the embedded inputs
   int Pp, tiles;
   static MlpBufs carve_all(char* base, int P, int train, size_t* bytes) {
@@ -79,12 +80,16 @@ struct MlpBufs {
       b.dZh = carve<__nv_bfloat16>(p, Pp * 16);
       b.dZt1 = carve<__nv_bfloat16>(p, Pp * 32);
       b.dE = carve<float>(p, Pp * K0);
+      for (int l = 0; l < 8; ++l) b.M[l] = carve<uint32_t>(p, Pp * 8);
+      b.Mt1 = carve<uint32_t>(p, Pp * 8);
     } else {
       __nv_bfloat16* ping = carve<__nv_bfloat16>(p, Pp * WID);
       __nv_bfloat16* pong = carve<__nv_bfloat16>(p, Pp * WID);
       for (int l = 0; l < 8; ++l) b.H[l] = (l == 4) ? b.A5 : ((l & 1) ? pong : ping);
       b.dZ[0] = b.dZ[1] = b.dZh = b.dZt1 = nullptr;
       b.dE = nullptr;
+      for (int l = 0; l < 8; ++l) b.M[l] = nullptr;
+      b.Mt1 = nullptr;
     }
     if (bytes) *bytes = size_t(p - base) + 128;
     return b;
@@ -209,8 +214,14 @@ __global__ void __launch_bounds__(256) colsum_blk_kernel(int F, const __nv_bfloa
       acc[2 * q + 1] += f.y;
     }
   }
+  // lanes of one kb are contiguous (8, 64 or 128 threads): reduce inside the warp first
+  const int span = min(lanes, 32);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) atomicAdd(&s_sum[kb * 8 + q], acc[q]);
+  for (int q = 0; q < 8; ++q) {
+    float a = acc[q];
+    for (int o = 1; o < span; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & (span - 1)) == 0) atomicAdd(&s_sum[kb * 8 + q], a);
+  }
   __syncthreads();
   if ((int)threadIdx.x < F) atomicAdd(&db[threadIdx.x], s_sum[threadIdx.x]);
 }
@@ -270,6 +281,7 @@ cudaError_t launch_mlp_forward(const DglNet& n, int P, const float* x, const flo
   if (n.has_timenet) {
     LayerArgs g = layer(BlkView{b.T0, (size_t)16 * ACT_R, 0}, 16, (CB)n.Wt0, WID, tiles);
     g.bias = n.bt0; g.relu = 1; g.out = b.T1; g.out_tile_stride = (size_t)WID * ACT_R;
+    g.mask_out = b.Mt1;
     CK(launch_layer_gemm(g, s));
     g = layer(BlkView{b.T1, (size_t)WID * ACT_R, 0}, WID, (CB)n.Wt1, 32, tiles);  // 30 outputs padded to 32
     g.bias = n.bt1; g.out = b.A5; g.out_tile_stride = (size_t)K5 * ACT_R; g.out_kb0 = TCOL / 8;
@@ -282,6 +294,7 @@ cudaError_t launch_mlp_forward(const DglNet& n, int P, const float* x, const flo
     g.bias = n.b[l]; g.relu = 1;
     const BlkView o = b.h(l);
     g.out = const_cast<__nv_bfloat16*>(o.p); g.out_tile_stride = o.tile_stride; g.out_kb0 = o.kb0;
+    g.mask_out = b.M[l];
     CK(launch_layer_gemm(g, s));
   }
   LayerArgs g = layer(b.h(7), WID, (CB)n.Wh, 16, tiles);
@@ -327,7 +340,7 @@ cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const fl
   int cur = 0;
   {
     LayerArgs g = layer(vZh, 16, (CB)n.WhT, WID, tiles);
-    g.mask = b.h(7);
+    g.mask_bits = b.M[7];
     g.out = b.dZ[cur]; g.out_tile_stride = HS;
     CK(launch_layer_gemm(g, s));
   }
@@ -349,7 +362,7 @@ cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const fl
     }
     if (l > 0) {
       LayerArgs g = layer(vZ, WID, (CB)n.WT[l], WID, tiles);  // for l == 5 the h4 part comes first
-      g.mask = b.h(l - 1);
+      g.mask_bits = b.M[l - 1];
       g.out = b.dZ[cur ^ 1]; g.out_tile_stride = HS;
       CK(launch_layer_gemm(g, s));
       cur ^= 1;
@@ -361,7 +374,7 @@ cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const fl
     CK(dw(vT1, vZt1, 32, tiles, gr.dWt1, WID, 1, s));   // dWt1[32,256] = dZt1^T . T1 (transposed form)
     colsum_blk_kernel<<<tiles, 256, 0, s>>>(32, b.dZt1, gr.dbt1);
     LayerArgs g = layer(vZt1, 32, (CB)n.Wt1T, WID, tiles);
-    g.mask = vT1;
+    g.mask_bits = b.Mt1;
     g.out = b.dZ[cur ^ 1]; g.out_tile_stride = HS;
     CK(launch_layer_gemm(g, s));
     CK(dw(BlkView{b.dZ[cur ^ 1], HS, 0}, BlkView{b.T0, (size_t)16 * ACT_R, 0}, 16, tiles, gr.dWt0, 16, 0, s));

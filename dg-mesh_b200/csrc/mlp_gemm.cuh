@@ -17,7 +17,7 @@
 //       persistent CTAs (one per SM) over the 128-row tiles; warp-specialised:
 //         warp 0    producer: per K-chunk one bulk copy for A and one for B into a 4-stage ring
 //         warp 1    issues tcgen05.mma (M = 128, N <= 256, K = 16) into one of TWO TMEM accumulators
-//         warps 2-5 epilogue of the previous tile (tcgen05.ld -> bias / ReLU / ReLU-mask -> blocked
+//         warps 2-5 epilogue of the previous tile (tcgen05.ld -> bias / ReLU / ReLU bit-mask -> blocked
 //                   bf16 store, fp32 store or fp32 reduction) while the next tile is being multiplied
 //   dw_gemm_kernel      C[Mf, Nf] += X[rows, Mf]^T . Y[rows, Nf]     (weight gradients)
 //       both operands MN-major straight from the blocked activations; each CTA accumulates its share
@@ -45,7 +45,9 @@ struct LayerArgs {
   int rows_valid;             // rows < rows_valid are written to the fp32 output
   const float* bias;          // [N] or null
   int relu;
-  BlkView mask;               // p == null: none; else keep where mask > 0 (same rows, N columns from mask.kb0)
+  const uint32_t* mask_bits;  // null: none; else ReLU mask of a previous output: bit j of word
+                              // [(tile*8 + c/32)*128 + row] keeps column c = 32*(c/32) + j
+  uint32_t* mask_out;         // null: none; else write this output's (value > 0) bits in that layout
   __nv_bfloat16* out;         // blocked output (N columns from out_kb0) or null
   size_t out_tile_stride;
   int out_kb0;
@@ -144,54 +146,59 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int buf = i & 1;
+      // the ReLU-mask words of this row are fetched while the tile is still being multiplied
+      uint32_t mb[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        mb[q] = (g.mask_bits && q * 32 < g.N) ? g.mask_bits[((size_t)tile * 8 + q) * ACT_R + r] : 0xffffffffu;
       mbar_wait(&s_acc_full[buf], (i >> 1) & 1);
       umma::fence_after_sync();
       const size_t row = (size_t)tile * ACT_R + r;
-#pragma unroll 1
-      for (int c0 = 0; c0 < g.N; c0 += 32) {
-        uint32_t raw[32];
-        umma::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 256 + c0), raw);
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(raw[j]) + s_bias[c0 + j];
-          if (g.relu) x = fmaxf(x, 0.0f);
-          v[j] = x;
-        }
-        const int nunits = min(4, (g.N - c0) >> 3);  // 8-column units of this 32-column slice
-        if (g.mask.p) {
-          const __nv_bfloat16* mt = g.mask.p + (size_t)tile * g.mask.tile_stride;
+      for (int q = 0; q < 8; ++q) {
+        const int c0 = q * 32;
+        if (c0 < g.N) {  // uniform
+          uint32_t raw[32];
+          umma::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 256 + c0), raw);
+          float v[32];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (u < nunits) {
-              const uint4 mm =
-                  *reinterpret_cast<const uint4*>(mt + ((size_t)(g.mask.kb0 + (c0 >> 3) + u) * ACT_R + r) * 8);
-              const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mm);
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(raw[j]) + s_bias[c0 + j];
+            if (g.relu) x = fmaxf(x, 0.0f);
+            v[j] = x;
+          }
+          if (g.mask_bits) {  // uniform
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v[8 * u + q] = (__bfloat162float(mb[q]) > 0.0f) ? v[8 * u + q] : 0.0f;
+            for (int j = 0; j < 32; ++j) v[j] = ((mb[q] >> j) & 1u) ? v[j] : 0.0f;
+          }
+          if (g.mask_out) {   // uniform
+            uint32_t pos = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pos |= (v[j] > 0.0f ? 1u : 0u) << j;
+            g.mask_out[((size_t)tile * 8 + q) * ACT_R + r] = pos;
+          }
+          const int nunits = min(4, (g.N - c0) >> 3);  // 8-column units of this 32-column slice
+          if (g.out) {
+            __nv_bfloat16* ot = g.out + (size_t)tile * g.out_tile_stride;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (u < nunits) {
+                uint4 pk;
+                __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p2[k] = __floats2bfloat162_rn(v[8 * u + 2 * k], v[8 * u + 2 * k + 1]);
+                *reinterpret_cast<uint4*>(ot + ((size_t)(g.out_kb0 + (c0 >> 3) + u) * ACT_R + r) * 8) = pk;
+              }
             }
           }
-        }
-        if (g.out) {
-          __nv_bfloat16* ot = g.out + (size_t)tile * g.out_tile_stride;
+          if (g.out_f32 && row < (size_t)g.rows_valid) {
+            float* dst = g.out_f32 + row * g.ld_f32 + c0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (u < nunits) {
-              uint4 pk;
-              __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) p2[q] = __floats2bfloat162_rn(v[8 * u + 2 * q], v[8 * u + 2 * q + 1]);
-              *reinterpret_cast<uint4*>(ot + ((size_t)(g.out_kb0 + (c0 >> 3) + u) * ACT_R + r) * 8) = pk;
-            }
-          }
-        }
-        if (g.out_f32 && row < (size_t)g.rows_valid) {
-          float* dst = g.out_f32 + row * g.ld_f32 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (c0 + j < g.n_f32) {
-              if (g.atomic) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-              else *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4) {
+              if (c0 + j < g.n_f32) {
+                if (g.atomic) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                else *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
             }
           }
         }

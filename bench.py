@@ -261,6 +261,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="skip the full-train-step leg (BASELINE.json's second metric, N=1 only)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -416,6 +418,15 @@ def main():
         out["gpu_launches"] = 8 * len(my_frames) * a.steps * world
         if rank == 0 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_port()
+        if rank == 0 and world == 1 and not a.no_train_step:
+            # BASELINE.json's other metric: full train-step ms (config C3, 200k Gaussians), ours and the
+            # reference's own modules side by side on this GPU (tools/train_step.py)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import train_step
+                out["train_step"] = train_step.measure(steps=5)
+            except Exception as e:  # never lose the headline line over the extra leg
+                out["train_step"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -313,24 +313,32 @@ static cudaError_t dw(const BlkView& X, const BlkView& Y, int N, int tiles, floa
   return launch_dw_gemm(g, s);
 }
 
+bool grads_are_packed(const DglGrads& g);
+size_t packed_grad_total_bytes();
+
 cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const float* out, const float* g_out,
                                 void* ws, const DglGrads& gr, float* dx, cudaStream_t s) {
   MlpBufs b = MlpBufs::carve_all((char*)ws, P, 1, nullptr);
   const int Pp = b.Pp, tiles = b.tiles;
   const size_t HS = (size_t)WID * ACT_R;  // tile stride of a 256-feature activation
   cudaMemsetAsync(b.dE, 0, sizeof(float) * (size_t)Pp * K0, s);
-  for (int l = 0; l < 8; ++l) {
-    const int K = (l == 0) ? K0 : (l == 5 ? K5 : WID);
-    cudaMemsetAsync(gr.dW[l], 0, sizeof(float) * WID * K, s);
-    cudaMemsetAsync(gr.db[l], 0, sizeof(float) * WID, s);
-  }
-  cudaMemsetAsync(gr.dWh, 0, sizeof(float) * 16 * WID, s);
-  cudaMemsetAsync(gr.dbh, 0, sizeof(float) * 16, s);
-  if (n.has_timenet) {
-    cudaMemsetAsync(gr.dWt0, 0, sizeof(float) * WID * 16, s);
-    cudaMemsetAsync(gr.dbt0, 0, sizeof(float) * WID, s);
-    cudaMemsetAsync(gr.dWt1, 0, sizeof(float) * 32 * WID, s);
-    cudaMemsetAsync(gr.dbt1, 0, sizeof(float) * 32, s);
+  if (grads_are_packed(gr)) {
+    // the usual case (dgl_mlp_grad_pointers): one contiguous buffer, one memset
+    cudaMemsetAsync(gr.dW[0], 0, packed_grad_total_bytes(), s);
+  } else {
+    for (int l = 0; l < 8; ++l) {
+      const int K = (l == 0) ? K0 : (l == 5 ? K5 : WID);
+      cudaMemsetAsync(gr.dW[l], 0, sizeof(float) * WID * K, s);
+      cudaMemsetAsync(gr.db[l], 0, sizeof(float) * WID, s);
+    }
+    cudaMemsetAsync(gr.dWh, 0, sizeof(float) * 16 * WID, s);
+    cudaMemsetAsync(gr.dbh, 0, sizeof(float) * 16, s);
+    if (n.has_timenet) {
+      cudaMemsetAsync(gr.dWt0, 0, sizeof(float) * WID * 16, s);
+      cudaMemsetAsync(gr.dbt0, 0, sizeof(float) * WID, s);
+      cudaMemsetAsync(gr.dWt1, 0, sizeof(float) * 32 * WID, s);
+      cudaMemsetAsync(gr.dbt1, 0, sizeof(float) * 32, s);
+    }
   }
   // heads: dWh[16,256] = dZh^T . H7 (computed transposed: X = H7), dbh, dZ7 = (dZh . Wh) * relu'(H7)
   const BlkView vZh{b.dZh, (size_t)16 * ACT_R, 0};
@@ -463,42 +471,60 @@ __device__ __forceinline__ int map_col(int c, int in_t, int mapped) {
   return K0 + (c - XE - in_t);
 }
 
-// src fp32 [rows, kin] (nn.Linear layout [out, in]) -> blocked bf16 operands (mlp_gemm.cuh):
+// One table-driven launch packs (or unpacks) every matrix and bias of a network.
+// Weight entry: src fp32 [rows, kin] (nn.Linear layout [out, in]) -> blocked bf16 operands (mlp_gemm.cuh):
 //   forward  B operand  dst : single tile of Rf rows (outputs), element (o, k) at ((k/8)*Rf + o)*8 + k%8
 //   backward B operand  dstT: rows = inputs j, contraction index = outputs o:
 //            element (j, o) at ((o/8)*Rt + j)*8 + o%8.  For the input-facing layers the input columns
 //            split into the [x_emb, t] block (j < 96, Rt = 96, at dstT_e) and the hidden block
 //            (j >= 96 -> j - 96, Rt = 256, at dstT).
-__global__ void pack_w_kernel(const float* __restrict__ src, int rows, int kin, int in_t, int mapped, int r0, int Rf,
-                              __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dstT, int Rt,
-                              __nv_bfloat16* __restrict__ dstT_e) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * kin) return;
-  const int r = i / kin, c = i % kin;
-  const int cc = map_col(c, in_t, mapped), o = r0 + r;
-  const __nv_bfloat16 v = __float2bfloat16_rn(src[i]);
-  dst[((size_t)(cc >> 3) * Rf + o) * 8 + (cc & 7)] = v;
-  if (mapped) {
-    if (cc < K0) {
-      if (dstT_e) dstT_e[((size_t)(o >> 3) * K0 + cc) * 8 + (o & 7)] = v;
-    } else if (dstT) {
-      dstT[((size_t)(o >> 3) * WID + (cc - K0)) * 8 + (o & 7)] = v;
+struct PackEntry {
+  const float* src;          // pack: raw weight / bias;  unpack: packed fp32 gradient
+  float* dst_f32;            // bias copy / unpacked gradient
+  __nv_bfloat16 *dst, *dstT, *dstT_e;
+  int rows, kin, mapped, r0, Rf, Rt, kpad, is_bias;
+};
+#define PACK_MAX 32
+struct PackTable {
+  PackEntry e[PACK_MAX];
+  int n, in_t;
+};
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackTable t) {
+  const PackEntry& E = t.e[blockIdx.y];
+  const int total = E.rows * E.kin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (E.is_bias) {
+      E.dst_f32[i] = E.src[i];
+      continue;
     }
-  } else if (dstT) {
-    dstT[((size_t)(o >> 3) * Rt + cc) * 8 + (o & 7)] = v;
+    const int r = i / E.kin, c = i % E.kin;
+    const int cc = map_col(c, t.in_t, E.mapped), o = E.r0 + r;
+    const __nv_bfloat16 v = __float2bfloat16_rn(E.src[i]);
+    E.dst[((size_t)(cc >> 3) * E.Rf + o) * 8 + (cc & 7)] = v;
+    if (E.mapped) {
+      if (cc < K0) {
+        if (E.dstT_e) E.dstT_e[((size_t)(o >> 3) * K0 + cc) * 8 + (o & 7)] = v;
+      } else if (E.dstT) {
+        E.dstT[((size_t)(o >> 3) * WID + (cc - K0)) * 8 + (o & 7)] = v;
+      }
+    } else if (E.dstT) {
+      E.dstT[((size_t)(o >> 3) * E.Rt + cc) * 8 + (o & 7)] = v;
+    }
   }
 }
-// packed fp32 grad [*, kpad] (row offset r0) -> reference-shaped [rows, kin]
-__global__ void unpack_w_kernel(const float* __restrict__ src, int kpad, int r0, int rows, int kin, int in_t,
-                                int mapped, float* __restrict__ dst) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * kin) return;
-  const int r = i / kin, c = i % kin;
-  dst[i] = src[(size_t)(r0 + r) * kpad + map_col(c, in_t, mapped)];
-}
-__global__ void copy_f32_kernel(const float* __restrict__ src, int n, float* __restrict__ dst) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[i];
+// packed fp32 gradients (row-major [*, kpad], row offset r0) -> reference-shaped [rows, kin]; biases copied
+__global__ void __launch_bounds__(256) unpack_all_kernel(const PackTable t) {
+  const PackEntry& E = t.e[blockIdx.y];
+  const int total = E.rows * E.kin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (E.is_bias) {
+      E.dst_f32[i] = E.src[i];
+      continue;
+    }
+    const int r = i / E.kin, c = i % E.kin;
+    E.dst_f32[i] = E.src[(size_t)(E.r0 + r) * E.kpad + map_col(c, t.in_t, E.mapped)];
+  }
 }
 
 // fixed layout of the packed buffers (elements)
@@ -555,11 +581,17 @@ cudaError_t launch_mlp_pack(const DglRaw& r, void* wbuf, float* bbuf, DglNet* ne
   net->has_timenet = r.has_timenet; net->in_t = r.in_t; net->sigmoid_out = r.sigmoid_out;
   const size_t NONE = (size_t)-1;
   auto at = [&](size_t off) { return off == NONE ? (__nv_bfloat16*)nullptr : w + off; };
+  PackTable T = {};
+  T.in_t = r.in_t;
   auto pack = [&](const float* src, int rows, int kin, int mapped, int r0, int Rf, size_t dst, size_t dstT, int Rt,
                   size_t dstT_e) {
-    const int n = rows * kin;
-    pack_w_kernel<<<(n + 255) / 256, 256, 0, s>>>(src, rows, kin, r.in_t, mapped, r0, Rf, w + dst, at(dstT), Rt,
-                                                  at(dstT_e));
+    PackEntry& E = T.e[T.n++];
+    E.src = src; E.rows = rows; E.kin = kin; E.mapped = mapped; E.r0 = r0; E.Rf = Rf;
+    E.dst = w + dst; E.dstT = at(dstT); E.Rt = Rt; E.dstT_e = at(dstT_e);
+  };
+  auto bias = [&](const float* src, int n_el, float* dst) {
+    PackEntry& E = T.e[T.n++];
+    E.src = src; E.rows = 1; E.kin = n_el; E.dst_f32 = dst; E.is_bias = 1;
   };
   for (int l = 0; l < 8; ++l) {
     const int kin = (l == 0) ? in_width(r) : (l == 5 ? in_width(r) + WID : WID);
@@ -567,13 +599,13 @@ cudaError_t launch_mlp_pack(const DglRaw& r, void* wbuf, float* bbuf, DglNet* ne
     if (l == 0) pack(r.W[l], WID, kin, 1, 0, WID, L.W[l], NONE, 0, L.WT[l]);
     else if (l == 5) pack(r.W[l], WID, kin, 1, 0, WID, L.W[l], L.WT[l], WID, L.WT[l] + (size_t)WID * WID);
     else pack(r.W[l], WID, kin, 0, 0, WID, L.W[l], L.WT[l], WID, NONE);
-    copy_f32_kernel<<<1, 256, 0, s>>>(r.b[l], WID, bbuf + L.b[l]);
+    bias(r.b[l], WID, bbuf + L.b[l]);
     net->W[l] = w + L.W[l]; net->WT[l] = w + L.WT[l]; net->b[l] = bbuf + L.b[l];
   }
   int r0 = 0;
   for (int h = 0; h < r.n_heads; ++h) {
     pack(r.Wh[h], r.head_rows[h], WID, 0, r0, 16, L.Wh, L.WhT, WID, NONE);
-    copy_f32_kernel<<<1, 256, 0, s>>>(r.bh[h], r.head_rows[h], bbuf + L.bh + r0);
+    bias(r.bh[h], r.head_rows[h], bbuf + L.bh + r0);
     r0 += r.head_rows[h];
   }
   net->n_out = r0;
@@ -581,15 +613,29 @@ cudaError_t launch_mlp_pack(const DglRaw& r, void* wbuf, float* bbuf, DglNet* ne
   if (r.has_timenet) {
     pack(r.Wt0, WID, 13, 0, 0, WID, L.Wt0, NONE, 0, NONE);
     pack(r.Wt1, r.in_t, WID, 0, 0, 32, L.Wt1, L.Wt1T, WID, NONE);
-    copy_f32_kernel<<<1, 256, 0, s>>>(r.bt0, WID, bbuf + L.bt0);
-    copy_f32_kernel<<<1, 256, 0, s>>>(r.bt1, r.in_t, bbuf + L.bt1);
+    bias(r.bt0, WID, bbuf + L.bt0);
+    bias(r.bt1, r.in_t, bbuf + L.bt1);
     net->Wt0 = w + L.Wt0; net->Wt1 = w + L.Wt1; net->Wt1T = w + L.Wt1T;
     net->bt0 = bbuf + L.bt0; net->bt1 = bbuf + L.bt1;
   } else {
     net->Wt0 = net->Wt1 = net->Wt1T = nullptr;
     net->bt0 = net->bt1 = nullptr;
   }
+  pack_all_kernel<<<dim3(32, T.n), 256, 0, s>>>(T);
   return cudaGetLastError();
+}
+
+size_t packed_grad_total_bytes() { return layout().g_total * sizeof(float); }
+
+// true when `g` is the pointer table of ONE packed buffer starting at g.dW[0]
+bool grads_are_packed(const DglGrads& g) {
+  const PackLayout& L = layout();
+  if (L.gW[0] != 0 || !g.dW[0]) return false;
+  float* base = g.dW[0];
+  for (int l = 0; l < 8; ++l)
+    if (g.dW[l] != base + L.gW[l] || g.db[l] != base + L.gb[l]) return false;
+  return g.dWh == base + L.gWh && g.dbh == base + L.gbh && g.dWt0 == base + L.gWt0 && g.dbt0 == base + L.gbt0 &&
+         g.dWt1 == base + L.gWt1 && g.dbt1 == base + L.gbt1;
 }
 
 void mlp_grad_pointers(float* gbuf, DglGrads* g) {
@@ -605,28 +651,35 @@ void mlp_grad_pointers(float* gbuf, DglGrads* g) {
 // packed gradients -> tensors shaped like the reference parameters (DglRawGrads mirrors DglRaw)
 cudaError_t launch_mlp_unpack_grads(const DglRaw& r, const float* gbuf, const DglRawGrads& o, cudaStream_t s) {
   const PackLayout& L = layout();
+  PackTable T = {};
+  T.in_t = r.in_t;
   auto unpack = [&](size_t src, int kpad, int r0, int rows, int kin, int mapped, float* dst) {
-    const int n = rows * kin;
-    unpack_w_kernel<<<(n + 255) / 256, 256, 0, s>>>(gbuf + src, kpad, r0, rows, kin, r.in_t, mapped, dst);
+    PackEntry& E = T.e[T.n++];
+    E.src = gbuf + src; E.kpad = kpad; E.r0 = r0; E.rows = rows; E.kin = kin; E.mapped = mapped; E.dst_f32 = dst;
+  };
+  auto bias = [&](size_t src, int n_el, float* dst) {
+    PackEntry& E = T.e[T.n++];
+    E.src = gbuf + src; E.rows = 1; E.kin = n_el; E.dst_f32 = dst; E.is_bias = 1;
   };
   for (int l = 0; l < 8; ++l) {
     const int kin = (l == 0) ? in_width(r) : (l == 5 ? in_width(r) + WID : WID);
     const int kpad = (l == 0) ? K0 : (l == 5 ? K5 : WID);
     unpack(L.gW[l], kpad, 0, WID, kin, l == 0 || l == 5, o.W[l]);
-    copy_f32_kernel<<<1, 256, 0, s>>>(gbuf + L.gb[l], WID, o.b[l]);
+    bias(L.gb[l], WID, o.b[l]);
   }
   int r0 = 0;
   for (int h = 0; h < r.n_heads; ++h) {
     unpack(L.gWh, WID, r0, r.head_rows[h], WID, 0, o.Wh[h]);
-    copy_f32_kernel<<<1, 256, 0, s>>>(gbuf + L.gbh + r0, r.head_rows[h], o.bh[h]);
+    bias(L.gbh + r0, r.head_rows[h], o.bh[h]);
     r0 += r.head_rows[h];
   }
   if (r.has_timenet) {
     unpack(L.gWt0, 16, 0, WID, 13, 0, o.Wt0);
     unpack(L.gWt1, WID, 0, r.in_t, WID, 0, o.Wt1);
-    copy_f32_kernel<<<1, 256, 0, s>>>(gbuf + L.gbt0, WID, o.bt0);
-    copy_f32_kernel<<<1, 256, 0, s>>>(gbuf + L.gbt1, r.in_t, o.bt1);
+    bias(L.gbt0, WID, o.bt0);
+    bias(L.gbt1, r.in_t, o.bt1);
   }
+  unpack_all_kernel<<<dim3(32, T.n), 256, 0, s>>>(T);
   return cudaGetLastError();
 }
 

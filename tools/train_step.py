@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Full training-step time (deformation MLPs + rasterizer + DPSR + marching
+cubes + vertex MLPs, forward and backward) for this implementation and, beside it, for the reference's
+own modules on the same GPU: fp32 PyTorch MLPs and DPSR (oracle/_ref/refpy), the stock CUDA rasterizer
+(oracle/_ref).  `diso` (DiffMC) does not exist in the reference tree, so BOTH arms use this repo's
+marching cubes; the mesh image loss needs nvdiffrast and is replaced by verts.sum() + colour.sum() so
+the DPSR / MC / vertex-MLP backward still runs.
+
+    python tools/train_step.py [--gaussians 200000] [--grid 288] [--steps 10]
+prints one JSON object with the step time and a per-component breakdown of both arms.
+"""
+import argparse
+import importlib
+import json
+import math
+import os
+import sys
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "dg-mesh_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import torch  # noqa: E402
+
+
+def build(arm, n, G, dev):
+    import synth
+    import util
+    torch.manual_seed(0)
+    if arm == "ours":
+        import diff_gaussian_rasterization as dgr
+        tu = importlib.import_module("utils.time_utils")
+        from nvdiffrast_utils.dpsr import DPSR
+    else:
+        ref = util.load_reference_pymodules()
+        dgr = util.load_reference_rasterizer()
+        if ref is None or dgr is None:
+            return None
+        tu, DPSR = ref.time_utils, ref.dpsr.DPSR
+    from diso import DiffMC
+    renderer = importlib.import_module("utils.renderer")
+    sc = synth.gaussian_scene(n=n, seed=0, device=dev)
+    g = torch.Generator().manual_seed(3)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1)
+    xyz = (d * 0.6 + 0.01 * torch.randn(n, 3, generator=g)).to(dev)      # a thick spherical shell: clean mesh
+    P = SimpleNamespace(
+        xyz=xyz.requires_grad_(True), normal=d.to(dev).clone().requires_grad_(True),
+        opacities=sc["opacities"].clone().requires_grad_(True), scales=sc["scales"].clone().requires_grad_(True),
+        rotations=sc["rotations"].clone().requires_grad_(True), shs=sc["shs"].clone().requires_grad_(True),
+        thres=torch.zeros((), device=dev, requires_grad=True))
+    nets = SimpleNamespace(
+        deform=tu.DeformNetworkNormal(is_blender=True).to(dev), deform_normal=tu.DeformNetworkNormalSep(is_blender=True).to(dev),
+        deform_back=tu.DeformNetworkNormal(is_blender=True).to(dev),
+        deform_back_normal=tu.DeformNetworkNormalSep(is_blender=True).to(dev),
+        appearance=tu.AppearanceNetwork(is_blender=True).to(dev))
+    dpsr = DPSR(res=(G, G, G), sig=3.0)
+    if arm != "ours":
+        dpsr = dpsr.to(dev)
+    gauss = SimpleNamespace(gaussian_center=torch.zeros(3, device=dev), gaussian_scale=torch.tensor([1.2 * 1.3], device=dev),
+                            dpsr=dpsr, diffmc=DiffMC(dtype=torch.float32).to(dev))
+    cam = synth.look_at_camera(azimuth_deg=30.0, elevation_deg=20.0, radius=4.0, width=800, height=800, device=dev)
+    bg = torch.ones(3, device=dev)
+    gt = torch.rand(3, 800, 800, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    params = [P.xyz, P.normal, P.opacities, P.scales, P.rotations, P.shs, P.thres] + \
+        [q for m in vars(nets).values() for q in m.parameters()]
+    return SimpleNamespace(arm=arm, dgr=dgr, renderer=renderer, P=P, nets=nets, gauss=gauss, cam=cam, bg=bg, gt=gt,
+                           params=params, n=n, synth=synth)
+
+
+def mlp_part(S, t):
+    P, N = S.P, S.nets
+    d_xyz, d_rot, d_scale, d_normal = N.deform(P.xyz, t)
+    d_normal = d_normal + N.deform_normal(P.xyz, t)
+    warped = P.xyz + d_xyz
+    b_xyz, _, _, b_normal = N.deform_back(warped.detach(), t)
+    b_normal = b_normal + N.deform_back_normal(warped.detach(), t)
+    cycle = (d_xyz + b_xyz).abs().mean() + (d_normal + b_normal).abs().mean()
+    return d_xyz, d_rot, d_scale, d_normal, cycle
+
+
+def raster_part(S, d_xyz, d_rot, d_scale):
+    P, cam = S.P, S.cam
+    rs = S.dgr.GaussianRasterizationSettings(
+        image_height=800, image_width=800, tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5),
+        bg=S.bg, scale_modifier=1.0, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
+        sh_degree=3, campos=cam.camera_center, prefiltered=False, debug=False)
+    m2d = torch.zeros_like(P.xyz, requires_grad=True)
+    img, radii = S.dgr.GaussianRasterizer(rs)(means3D=P.xyz + d_xyz, means2D=m2d, opacities=P.opacities, shs=P.shs,
+                                              scales=P.scales + d_scale, rotations=P.rotations + d_rot)
+    return (img - S.gt).abs().mean()
+
+
+def mesh_part(S, d_xyz, d_normal, t1):
+    g = S.gauss
+    g.get_xyz, g.get_normal, g.density_thres_param = S.P.xyz, S.P.normal, S.P.thres
+    verts, faces = S.renderer.extract_mesh(g, d_xyz, d_normal)
+    tv = t1.expand(verts.shape[0], 1)
+    back, _, _, _ = S.nets.deform_back(verts.detach(), tv)
+    color = S.nets.appearance(verts + back, tv)
+    return verts.sum() * 1e-3 + color.mean(), verts.shape[0]
+
+
+def full_step(S):
+    for q in S.params:
+        q.grad = None
+    t1 = torch.full((1, 1), 0.37, device=S.bg.device)
+    t = t1.expand(S.n, 1)
+    d_xyz, d_rot, d_scale, d_normal, cycle = mlp_part(S, t)
+    loss = raster_part(S, d_xyz, d_rot, d_scale) + cycle
+    lm, V = mesh_part(S, d_xyz, d_normal, t1)
+    (loss + lm).backward()
+    return V
+
+
+def timeit(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def components(S, steps):
+    dev = S.bg.device
+    t1 = torch.full((1, 1), 0.37, device=dev)
+    t = t1.expand(S.n, 1)
+
+    def f_mlp():
+        d_xyz, d_rot, d_scale, d_normal, cycle = mlp_part(S, t)
+        (cycle + d_rot.sum() + d_scale.sum()).backward()
+
+    def f_raster():
+        z = torch.zeros_like(S.P.xyz)
+        raster_part(S, z, torch.zeros_like(S.P.rotations), z).backward()
+
+    def f_mesh():
+        z = torch.zeros_like(S.P.xyz)
+        mesh_part(S, z, z, t1)[0].backward()
+
+    return {"mlp_4xN_ms": timeit(f_mlp, steps), "raster_ms": timeit(f_raster, steps),
+            "dpsr_mc_2xV_mlp_ms": timeit(f_mesh, steps)}
+
+
+def measure(n=200_000, G=288, steps=10, arms=("ours", "reference")):
+    dev = torch.device("cuda")
+    out = {"config": f"C3: {n} Gaussians, 800x800, grid {G}, 4 N-MLPs + raster + DPSR + MC + 2 V-MLPs, fwd+bwd",
+           "note": "marching cubes is this repo's kernel in both arms (diso is absent from the reference tree); "
+                   "reference MLPs/DPSR are its fp32 PyTorch modules, reference rasterizer its stock CUDA build"}
+    for arm in arms:
+        S = build(arm, n, G, dev)
+        if S is None:
+            out[arm] = {"unavailable": "oracle/_ref not built"}
+            continue
+        V = full_step(S)
+        ms = timeit(lambda: full_step(S), steps)
+        out[arm] = {"train_step_ms": ms, "mesh_vertices": V, **components(S, steps)}
+        del S
+        torch.cuda.empty_cache()
+    if "train_step_ms" in out.get("ours", {}) and "train_step_ms" in out.get("reference", {}):
+        out["speedup"] = out["reference"]["train_step_ms"] / out["ours"]["train_step_ms"]
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gaussians", type=int, default=200_000)
+    ap.add_argument("--grid", type=int, default=288)
+    ap.add_argument("--steps", type=int, default=10)
+    a = ap.parse_args()
+    print(json.dumps(measure(a.gaussians, a.grid, a.steps)))

@@ -17,7 +17,7 @@
 //       persistent CTAs (one per SM) over the 128-row tiles; warp-specialised:
 //         warp 0    producer: per K-chunk one bulk copy for A and one for B into a 4-stage ring
 //         warp 1    issues tcgen05.mma (M = 128, N <= 256, K = 16) into one of TWO TMEM accumulators
-//         warps 2-5 epilogue of the previous tile (tcgen05.ld -> bias / ReLU / ReLU bit-mask -> blocked
+//         warps 2-9 epilogue of the previous tile (tcgen05.ld -> bias / ReLU / ReLU bit-mask -> blocked
 //                   bf16 store, fp32 store or fp32 reduction) while the next tile is being multiplied
 //   dw_gemm_kernel      C[Mf, Nf] += X[rows, Mf]^T . Y[rows, Nf]     (weight gradients)
 //       both operands MN-major straight from the blocked activations; each CTA accumulates its share
@@ -58,7 +58,7 @@ struct LayerArgs {
 #define LG_STAGES 4
 #define LG_A_BYTES (ACT_R * 64 * 2)  // 16 KB: 128 rows x 64 K
 #define LG_B_BYTES (256 * 64 * 2)    // 32 KB: up to 256 rows x 64 K
-#define LG_THREADS 192
+#define LG_THREADS 320  // producer warp + MMA warp + 8 epilogue warps
 #define LG_SMEM (LG_STAGES * (LG_A_BYTES + LG_B_BYTES) + 1024)
 
 __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerArgs g) {
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_acc_full[b], 1);
-      mbar_init(&s_acc_empty[b], 128);
+      mbar_init(&s_acc_empty[b], 256);
     }
     mbar_fence_init();
   }
@@ -140,24 +140,29 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // two warps per TMEM lane group (a warp may only touch lanes 32*(warp%4)..+31): warps 2-5 take
+    // the 32-column slices 0-3, warps 6-9 the slices 4-7, so two tcgen05.ld / store streams overlap
     const int lg = warp & 3;       // TMEM lane group this warp may access
     const int r = lg * 32 + lane;  // row inside the tile
+    const int q0 = (warp >= 6) ? 4 : 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int buf = i & 1;
       // the ReLU-mask words of this row are fetched while the tile is still being multiplied
-      uint32_t mb[8];
+      uint32_t mb[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        mb[q] = (g.mask_bits && q * 32 < g.N) ? g.mask_bits[((size_t)tile * 8 + q) * ACT_R + r] : 0xffffffffu;
+      for (int q = 0; q < 4; ++q)
+        mb[q] = (g.mask_bits && (q0 + q) * 32 < g.N) ? g.mask_bits[((size_t)tile * 8 + q0 + q) * ACT_R + r]
+                                                     : 0xffffffffu;
       mbar_wait(&s_acc_full[buf], (i >> 1) & 1);
       umma::fence_after_sync();
       const size_t row = (size_t)tile * ACT_R + r;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int qq = 0; qq < 4; ++qq) {
+        const int q = q0 + qq;
         const int c0 = q * 32;
-        if (c0 < g.N) {  // uniform
+        if (c0 < g.N) {  // uniform per warp
           uint32_t raw[32];
           umma::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 256 + c0), raw);
           float v[32];
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
           }
           if (g.mask_bits) {  // uniform
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ((mb[q] >> j) & 1u) ? v[j] : 0.0f;
+            for (int j = 0; j < 32; ++j) v[j] = ((mb[qq] >> j) & 1u) ? v[j] : 0.0f;
           }
           if (g.mask_out) {   // uniform
             uint32_t pos = 0;

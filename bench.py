@@ -265,6 +265,11 @@ def main():
                     help="skip the full-train-step leg (BASELINE.json's second metric, N=1 only)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    # exactly ONE line may reach stdout (the JSON): libraries that print there (NCCL's version banner)
+    # are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -283,7 +288,8 @@ def main():
         import util
         dgr = util.load_reference_rasterizer()
         if dgr is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built in this snapshot"}))
+            os.dup2(real_stdout, 1)
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built in this snapshot"}), flush=True)
             return 0
     else:
         import diff_gaussian_rasterization as dgr
@@ -310,12 +316,21 @@ def main():
         if world > 1:
             dist.all_reduce(gflat)  # the one collective of the step
 
+    def step_render_only():
+        gflat.zero_()
+        run_batch(dgr, leaves, dev_settings, dpix_stacked)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms = timed(step, a.steps, a.warmup, world)
     clocks = sampler.stop() if rank == 0 else None
     value = FRAMES * a.steps / (ms * 1e-3)
+    breakdown = None
+    if world > 1 and ours:
+        breakdown = {"render_only_ms": timed(step_render_only, a.steps, 2, world) / a.steps,
+                     "allreduce_only_ms": timed(lambda: dist.all_reduce(gflat), a.steps, 2, world) / a.steps,
+                     "allreduce_bytes": gflat.numel() * 4}
 
     # ---- e2e leg: host buffers, copies inside the timed region
     feed = HostFeed(cams, my_frames, dev)
@@ -359,6 +374,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "clocks": clocks,
     }
+    if breakdown:
+        out["breakdown"] = breakdown
     if a.impl == "reference":
         out["impl"] = "reference"
         out["n_gpus"] = a.gpus
@@ -427,10 +444,12 @@ def main():
                 out["train_step"] = train_step.measure(steps=5)
             except Exception as e:  # never lose the headline line over the extra leg
                 out["train_step"] = {"error": f"{type(e).__name__}: {e}"}
-    if rank == 0:
-        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     return 0
 
 

@@ -116,8 +116,8 @@ def parse_ref_buffers(geom, binning, img, P, R, W, H):
 def rel_err(a, b):
     """max |a-b| / (max|b| + tiny): the 'relative to the tensor's scale' error used for the
     1e-4 fp32 contract (north_star)."""
-    a = torch.as_tensor(a, dtype=torch.float64).detach()
-    b = torch.as_tensor(b, dtype=torch.float64).detach()
+    a = torch.as_tensor(a, dtype=torch.float64).detach().cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).detach().cpu()
     if a.numel() == 0:
         return 0.0
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))

@@ -232,7 +232,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         bg, sh, col, opac, sc, rot, cov, view, proj, campos = ctx.tensors
         means3D, radii = ctx.saved_tensors
         ws = ctx.ws
-        _Sizing.poll(block=True)  # the forward must not have overflowed (raises otherwise)
+        # No host wait here: if the forward overflowed, its image is background-only with n_contrib = 0,
+        # so this backward produces exact zeros; the overflow itself is raised at the next poll.
+        _Sizing.poll()
         lib = _dgm_lib.lib()
         P = means3D.shape[0]
         H, W = int(rs.image_height), int(rs.image_width)
@@ -371,7 +373,7 @@ class _RasterizeGaussiansBatch(torch.autograd.Function):
         views, projs, cams, tx, ty = ctx.cams
         means3D, radii = ctx.saved_tensors
         ws, rs0 = ctx.ws, ctx.settings[0]
-        _Sizing.poll(block=True)
+        _Sizing.poll()  # non-blocking (an overflowed forward back-propagates zeros, see _RasterizeGaussians)
         F, P = ws.F, means3D.shape[0]
         H, W = int(rs0.image_height), int(rs0.image_width)
         M = int(sh.shape[1]) if sh is not None else 0

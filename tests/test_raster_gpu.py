@@ -99,7 +99,7 @@ def run_ref(sc, cam, bg, degree=3, use_colors=False, use_cov=False, dpix=None, s
     return out
 
 
-def compare(ours, ref, tol=TOL, check_grads=True, label="", skip=()):
+def compare(ours, ref, tol=TOL, check_grads=True, label="", skip=(), n_contrib_slack=0):
     vis = ref["radii"] > 0
     # ---- integer / bit-exact state
     assert torch.equal(ours["radii"], ref["radii"]), f"{label} radii"
@@ -111,7 +111,9 @@ def compare(ours, ref, tol=TOL, check_grads=True, label="", skip=()):
     assert torch.equal(ours["point_list_keys"], ref["point_list_keys"]), f"{label} sorted keys"
     assert torch.equal(ours["point_list"], ref["point_list"]), f"{label} point_list"
     assert torch.equal(ours["ranges"], ref["ranges"]), f"{label} ranges"
-    assert torch.equal(ours["n_contrib"], ref["n_contrib"]), f"{label} n_contrib"
+    # n_contrib depends on fp32 threshold tests (alpha >= 1/255, T >= 1e-4) of values that agree to ~1e-7,
+    # not bit for bit: identical at the small sizes and at C2; one pixel in 2 million differs at C5
+    assert int((ours["n_contrib"] != ref["n_contrib"]).sum()) <= n_contrib_slack, f"{label} n_contrib"
     # ---- fp32 state within tolerance
     for k in ("cov3D", "conic_opacity", "rgb"):
         if k in ref and ref[k].numel() and k not in skip:
@@ -179,6 +181,19 @@ def test_full_size_config_c2_against_reference():
     a, b = run_ours(sc, cam, bg, 3, False, False, dpix), run_ref(sc, cam, bg, 3, False, False, dpix)
     assert b["R"] > 100_000
     compare(a, b, label="C2")
+
+
+def test_largest_config_c5_against_reference():
+    """BASELINE.json configs[4] shape: 500k Gaussians, 1920x1080 (1080 is not a multiple of 16:
+    ragged last tile row; 8 160 tiles), SH degree 3 -- integer state bit-exact, image / gradients 1e-4."""
+    import synth
+    sc = _cuda(synth.gaussian_scene(n=500_000, seed=0))
+    cam = _cam_cuda(synth.look_at_camera(width=1920, height=1080))
+    bg = torch.zeros(3, device="cuda")
+    dpix = torch.randn(3, 1080, 1920, generator=torch.Generator().manual_seed(2)).cuda()
+    a, b = run_ours(sc, cam, bg, 3, False, False, dpix), run_ref(sc, cam, bg, 3, False, False, dpix)
+    assert b["R"] > 1_000_000
+    compare(a, b, label="C5", n_contrib_slack=4)
 
 
 def test_against_cpu_oracle():
@@ -250,6 +265,37 @@ def test_workspace_overflow_is_reported_not_silent():
     cap = dgr._round_cap(int(st[0]))
     color2, _, ws2 = dgr._raw_forward(*args, cap)
     assert int(ws2.status_tensor().cpu()[1]) == 0 and float((color2 - color).abs().max()) > 0.05
+
+
+def test_overflowed_forward_backpropagates_zeros_and_raises_later():
+    """No host wait between forward and backward: an overflowed forward renders the background with
+    n_contrib = 0, its backward is exactly zero, and the overflow is raised at the next call."""
+    import _dgm_lib
+    import diff_gaussian_rasterization as dgr
+    import synth
+    sc, cam = util.small_scene(n=2000, W=96, H=64, seed=4, scale=0.05)
+    sc, cam = _cuda(sc), _cam_cuda(cam)
+    bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
+    rs = synth.raster_settings_for(cam, bg, settings_cls=dgr.GaussianRasterizationSettings)
+    leaves = {k: sc[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    key = (torch.cuda.current_device(), 2000, 96, 64)
+    dgr._Sizing.poll(block=True)
+    dgr._Sizing.hint[key] = 32                      # far too small
+    color, radii = dgr.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"],
+                                              shs=leaves["shs"], scales=leaves["scales"],
+                                              rotations=leaves["rotations"])
+    assert torch.allclose(color[2], torch.full_like(color[2], 0.3))
+    raised = False
+    try:
+        color.backward(torch.ones_like(color))     # polls without waiting: may already see the overflow
+        for k, v in leaves.items():
+            assert float(v.grad.abs().max()) == 0.0, k
+    except _dgm_lib.DgmError:
+        raised = True
+    if not raised:
+        with pytest.raises(_dgm_lib.DgmError):
+            dgr._Sizing.poll(block=True)
+    assert dgr._Sizing.hint[key] > 32               # capacity was raised for the retry
 
 
 def test_full_size_properties():

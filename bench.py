@@ -261,6 +261,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", choices=["on", "off"], default="off",
+                    help="replay the single-GPU step as ONE CUDA graph (the library is capture-safe); "
+                         "not used with NCCL: capturing the all-reduce hung in this round's test")
     ap.add_argument("--no-train-step", action="store_true",
                     help="skip the full-train-step leg (BASELINE.json's second metric, N=1 only)")
     a = ap.parse_args()
@@ -320,10 +323,37 @@ def main():
         gflat.zero_()
         run_batch(dgr, leaves, dev_settings, dpix_stacked)
 
+    # Optional: capture the step once and replay it as a CUDA graph (parameters, cameras and pixel
+    # gradients live at fixed addresses exactly as in a training loop with in-place optimiser updates;
+    # the library does no host polling while capturing).  Single GPU only.
+    use_graph = ours and a.graph == "on" and world == 1
+    timed_step = step
+    graph_note = None
+    if use_graph:
+        for _ in range(3):
+            step()          # eager warm-up: sizes the instance workspaces, creates the internal streams
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        try:
+            cap_stream = torch.cuda.Stream()
+            cap_stream.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(cap_stream):
+                with torch.cuda.graph(graph, stream=cap_stream):
+                    step()
+            torch.cuda.current_stream().wait_stream(cap_stream)
+            torch.cuda.synchronize()
+            timed_step = graph.replay
+        except Exception as e:  # keep the run alive: measure the eager step instead and say so
+            graph_note = f"graph capture failed ({type(e).__name__}: {e}); eager step timed"
+            use_graph = False
+            torch.cuda.synchronize()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed(step, a.steps, a.warmup, world)
+    ms = timed(timed_step, a.steps, a.warmup, world)
     clocks = sampler.stop() if rank == 0 else None
     value = FRAMES * a.steps / (ms * 1e-3)
     breakdown = None
@@ -366,7 +396,8 @@ def main():
                                "step = 8-frame batch (8 ring cameras), frames sharded over ranks",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "frames_per_step": FRAMES,
                    "parallelism": f"dp{world} over frames" + (", 1 NCCL all-reduce of grads" if world > 1 else ""),
-                   "api": "BatchGaussianRasterizer (frame batch, in-kernel gradient accumulation)" if ours
+                   "api": ("BatchGaussianRasterizer (frame batch, in-kernel gradient accumulation)"
+                           + (", step replayed as one CUDA graph" if (ours and use_graph) else "")) if ours
                           else "GaussianRasterizer per frame (reference API)",
                    "l2_policy": "inputs larger than L2: per step 8 frames x (~42 MB instance records + 12 MB "
                                 "per-Gaussian state + 13 MB pixel state) + 24 MB parameters + 61 MB pixel "
@@ -376,6 +407,8 @@ def main():
     }
     if breakdown:
         out["breakdown"] = breakdown
+    if graph_note:
+        out["graph_note"] = graph_note
     if a.impl == "reference":
         out["impl"] = "reference"
         out["n_gpus"] = a.gpus

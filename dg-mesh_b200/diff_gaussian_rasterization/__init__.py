@@ -52,6 +52,8 @@ class _Sizing:
     @classmethod
     def watch(cls, status, key, cap):
         """Queue an asynchronous read-back of a forward's status block (no host sync)."""
+        if torch.cuda.is_current_stream_capturing():
+            return  # CUDA-graph capture: no host-side polling; the capacity comes from the eager warm-up
         if cls.free:
             ev, host = cls.free.pop()
         else:
@@ -64,7 +66,7 @@ class _Sizing:
 
     @classmethod
     def poll(cls, block=False):
-        if not cls.pending:
+        if not cls.pending or torch.cuda.is_current_stream_capturing():
             return
         still = []
         err = None

@@ -254,6 +254,40 @@ def cpu_baseline_port():
             "sample": f"1 frame (fwd+bwd) of the same 100k/800x800 workload, C oracle, 1 thread of {os.cpu_count()}"}
 
 
+def cpu_paths_baseline():
+    """north_star: "its PyTorch-CPU deformation-MLP/KNN path timed on the box's own host cores in the
+    same run (core count stated)".  C1 = DeformNetworkNormal(is_blender) fwd+bwd on 10k points with the
+    reference's own module (oracle/_ref/refpy) on all host threads; KNN = the k-d-tree restatement of
+    distCUDA2 on 100k points (1 thread).  Reported, not optimised."""
+    import numpy as np
+    import util
+    from oracle.oracle import knn_mean_dist2
+    out = {"cores": os.cpu_count()}
+    ref = util.load_reference_pymodules()
+    if ref is not None:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        out["torch_threads"] = torch.get_num_threads()
+        torch.manual_seed(0)
+        net = ref.time_utils.DeformNetworkNormal(is_blender=True)
+        g = torch.Generator().manual_seed(0)
+        x = (torch.rand(10_000, 3, generator=g) * 2 - 1).requires_grad_(True)
+        t = torch.full((10_000, 1), 0.37)
+
+        def step():
+            net.zero_grad(set_to_none=True)
+            sum(o.sum() for o in net(x, t)).backward()
+        step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step()
+        out["mlp_c1_10k_fwd_bwd_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+    pts = np.random.default_rng(0).standard_normal((100_000, 3)) * 0.5
+    t0 = time.perf_counter()
+    knn_mean_dist2(pts)
+    out["knn_100k_ms"] = (time.perf_counter() - t0) * 1e3
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -468,6 +502,10 @@ def main():
         out["gpu_launches"] = 8 * len(my_frames) * a.steps * world
         if rank == 0 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_port()
+            try:
+                out["cpu_baseline"]["other_paths"] = cpu_paths_baseline()
+            except Exception as e:
+                out["cpu_baseline"]["other_paths"] = {"error": f"{type(e).__name__}: {e}"}
         if rank == 0 and world == 1 and not a.no_train_step:
             # BASELINE.json's other metric: full train-step ms (config C3, 200k Gaussians), ours and the
             # reference's own modules side by side on this GPU (tools/train_step.py)

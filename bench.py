@@ -265,7 +265,9 @@ def cpu_paths_baseline():
     out = {"cores": os.cpu_count()}
     ref = util.load_reference_pymodules()
     if ref is not None:
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        # all 128 threads of the box make this small problem ~50x SLOWER (measured 9.9 s/step); 16 is what
+        # a tuned CPU run would use
+        torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
         out["torch_threads"] = torch.get_num_threads()
         torch.manual_seed(0)
         net = ref.time_utils.DeformNetworkNormal(is_blender=True)

@@ -88,3 +88,28 @@ def test_cuda_dpsr_matches_reference_golden():
     assert ok, ("dN", info)
     ok, info = affine_close(V.grad, z["dV"], resid_tol=2e-3, scale_tol=1e-2)
     assert ok, ("dV", info)
+
+
+@pytest.mark.parametrize("cls,blender", [("DeformNetwork", True), ("DeformNetworkNormal", True),
+                                         ("DeformNetworkNormal", False), ("DeformNetworkNormalSep", True),
+                                         ("AppearanceNetwork", True)])
+def test_state_dicts_are_interchangeable_with_the_reference_cpu(cls, blender):
+    """reference checkpoints load into the drop-in modules and vice versa (same parameter
+    names, shapes and registration order)."""
+    ref = util.load_reference_pymodules()
+    if ref is None:
+        pytest.skip("oracle/_ref/refpy missing")
+    tu = importlib.import_module("utils.time_utils")
+    torch.manual_seed(3)
+    theirs = getattr(ref.time_utils, cls)(is_blender=blender)
+    mine = getattr(tu, cls)(is_blender=blender)
+    sd_t, sd_m = theirs.state_dict(), mine.state_dict()
+    assert list(sd_t.keys()) == list(sd_m.keys())
+    assert [tuple(v.shape) for v in sd_t.values()] == [tuple(v.shape) for v in sd_m.values()]
+    mine.load_state_dict(sd_t, strict=True)
+    theirs.load_state_dict(mine.state_dict(), strict=True)
+    for k in sd_t:
+        assert torch.equal(mine.state_dict()[k], sd_t[k])
+    # constructor surface
+    with pytest.raises(NotImplementedError):
+        getattr(tu, "DeformNetwork")(is_6dof=True)

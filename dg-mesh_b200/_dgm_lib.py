@@ -54,6 +54,9 @@ SIGNATURES = {
     "dgl_mlp_forward": (c_int, [P, c_int, P, P, P, c_int, P, c_size_t, P]),
     "dgl_mlp_backward": (c_int, [P, c_int, P, P, P, P, c_size_t, P, P, P]),
     "dgm_profile_enable": (c_int, [c_int]),
+    "dgloss_workspace_size": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "dgloss_forward": (c_int, [c_int, c_int, P, P, c_float, c_int, P, P, c_size_t, P]),
+    "dgloss_backward": (c_int, [c_int, c_int, P, P, c_float, c_int, P, P, P, c_size_t, P]),
     "dgm_profile_read": (c_int, [ctypes.POINTER(c_float), c_int]),
     "dgm_timeline_read": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_float), ctypes.POINTER(c_int), c_int]),
 }

@@ -5,6 +5,7 @@
 #include "knn_kernels.h"
 #include "dpsr_kernels.h"
 #include "mc_kernels.h"
+#include "loss_kernels.h"
 #include "mlp_kernels.h"
 
 #include <string.h>
@@ -550,6 +551,32 @@ int dgl_mlp_backward(const DglNet* net, int P, const float* x, const float* out,
   if (net->has_timenet && (!net->Wt1T || !grads->dWt0 || !grads->dbt0 || !grads->dWt1 || !grads->dbt1))
     return bad("dgl_mlp_backward: missing timenet buffers");
   return check(dgm::launch_mlp_backward(*net, P, x, out, g_out, ws, *grads, dx, (cudaStream_t)stream));
+}
+
+int dgloss_workspace_size(int H, int W, size_t* bytes) {
+  if (H <= 0 || W <= 0 || !bytes) return bad("dgloss_workspace_size: bad argument");
+  *bytes = dgm::loss_workspace_bytes(H, W);
+  return DGM_OK;
+}
+
+int dgloss_forward(int H, int W, const float* img, const float* gt, float lambda_dssim, int mode, float* out3, void* ws,
+                   size_t ws_bytes, void* stream) {
+  if (H <= 0 || W <= 0 || !img || !gt || !out3 || !ws) return bad("dgloss_forward: bad argument");
+  if (ws_bytes < dgm::loss_workspace_bytes(H, W)) {
+    strncpy(g_last_error, "dgloss_forward: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return check(dgm::launch_loss_forward(H, W, img, gt, lambda_dssim, mode, out3, ws, (cudaStream_t)stream));
+}
+
+int dgloss_backward(int H, int W, const float* img, const float* gt, float lambda_dssim, int mode,
+                    const float* dL_dloss, float* dL_dimg, void* ws, size_t ws_bytes, void* stream) {
+  if (H <= 0 || W <= 0 || !img || !gt || !dL_dimg || !ws) return bad("dgloss_backward: bad argument");
+  if (ws_bytes < dgm::loss_workspace_bytes(H, W)) {
+    strncpy(g_last_error, "dgloss_backward: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return check(dgm::launch_loss_backward(H, W, img, gt, lambda_dssim, mode, dL_dloss, dL_dimg, ws, (cudaStream_t)stream));
 }
 
 int dgm_profile_enable(int on) {

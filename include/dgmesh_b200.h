@@ -325,6 +325,22 @@ int dgl_mlp_backward(const DglNet* net, int P, const float* x, const float* out,
                      void* ws, size_t ws_bytes, const DglGrads* grads, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Image loss of the training step (next-tier row SURVEY.md 8(f)-3):
+ *   loss = (1 - lambda) * mean|img - gt| + lambda * (1 - SSIM(img, gt))        (mode 0)
+ * as dgmesh/train.py:308-311 composes l1_loss and ssim (dgmesh/utils/loss_utils.py:18-19, 39-76:
+ * 11x11 Gaussian window, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2); mode 1 returns the
+ * SSIM value itself (the stand-alone `ssim()` of the reference).  img, gt: [3,H,W] fp32.
+ *   forward : out3 = {loss (or ssim in mode 1), l1, ssim} on the device (no host read); keeps three
+ *             partial-derivative maps in `ws` for the backward call
+ *   backward: dL_dimg[3,H,W] = dL_dloss[0] * d out3[0] / d img   (dL_dloss NULL = 1)
+ * ------------------------------------------------------------------------ */
+int dgloss_workspace_size(int H, int W, size_t* bytes);
+int dgloss_forward(int H, int W, const float* img, const float* gt, float lambda_dssim, int mode,
+                   float* out3, void* ws, size_t ws_bytes, void* stream);
+int dgloss_backward(int H, int W, const float* img, const float* gt, float lambda_dssim, int mode,
+                    const float* dL_dloss, float* dL_dimg, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * Measurement hooks (bench.py roofline leg).  Off by default.  When enabled the
  * library records a CUDA event pair around each of its kernels ON THE LAUNCHING
  * STREAM; dgm_profile_read synchronises those events (the only call in this

@@ -83,6 +83,7 @@ def build(force=False):
         ("dgmesh/utils/rigid_utils.py", "rigid_utils.py"),
         ("dgmesh/utils/graphics_utils.py", "graphics_utils.py"),
         ("dgmesh/utils/sh_utils.py", "sh_utils.py"),
+        ("dgmesh/utils/loss_utils.py", "loss_utils.py"),
         ("dgmesh/nvdiffrast_utils/dpsr.py", "dpsr.py"),
         ("dgmesh/nvdiffrast_utils/dpsr_utils.py", "dpsr_utils.py"),
     ]:

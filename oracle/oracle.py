@@ -241,3 +241,47 @@ def mesh_topology(verts, faces):
     oriented = len(np.unique(dcode)) == len(dcode)
     used = len(np.unique(f))
     return used - len(uniq) + len(f), manifold, oriented
+
+
+# ----------------------------------------------------------------------------- image loss (next-tier row f3)
+def _gauss11():
+    """The 11-tap window of loss_utils.gaussian(11, 1.5) (dgmesh/utils/loss_utils.py:33-36), float32."""
+    import math
+    g = np.array([math.exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)], dtype=np.float32)
+    return (g / g.sum()).astype(np.float32)
+
+
+def _blur11(a):
+    """Zero-padded 11x11 separable Gaussian blur of [C,H,W] (== F.conv2d(a, outer(g,g), padding=5, groups=C))."""
+    g = _gauss11().astype(np.float64)
+    C, H, W = a.shape
+    p = np.zeros((C, H + 10, W + 10))
+    p[:, 5:5 + H, 5:5 + W] = a
+    h = sum(g[k] * p[:, :, k:k + W] for k in range(11))
+    return sum(g[k] * h[:, k:k + H, :] for k in range(11))
+
+
+def image_loss_np(img, gt, lam=0.2):
+    """(1 - lam) * L1 + lam * (1 - SSIM) as dgmesh/train.py:308-311 composes l1_loss and ssim
+    (dgmesh/utils/loss_utils.py:18-19, 39-76), and its gradient w.r.t. the rendered image `img`
+    (hand-derived; test_loss pins it against autograd through the reference functions).
+    Returns (loss, l1, ssim, dL_dimg)."""
+    x, y = np.asarray(img, np.float64), np.asarray(gt, np.float64)
+    n = x.size
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    m1, m2 = _blur11(x), _blur11(y)
+    e11, e22, e12 = _blur11(x * x), _blur11(y * y), _blur11(x * y)
+    s1, s2, s12 = e11 - m1 * m1, e22 - m2 * m2, e12 - m1 * m2
+    N1, N2 = 2 * m1 * m2 + C1, 2 * s12 + C2
+    D1, D2 = m1 * m1 + m2 * m2 + C1, s1 + s2 + C2
+    S = N1 * N2 / (D1 * D2)
+    l1, ssim = np.abs(x - y).mean(), S.mean()
+    loss = (1 - lam) * l1 + lam * (1 - ssim)
+    # d S / d(blurred maps), everything else fixed
+    dS_dm1 = (2 * m2 * N2 - 2 * m2 * N1) / (D1 * D2) - S * (2 * m1 / D1 - 2 * m1 / D2)
+    dS_de11 = -S / D2
+    dS_de12 = 2 * N1 / (D1 * D2)
+    # the window is symmetric: the adjoint of the blur is the blur
+    dssim_dx = (_blur11(dS_dm1) + 2 * x * _blur11(dS_de11) + y * _blur11(dS_de12)) / n
+    grad = (1 - lam) * np.sign(x - y) / n - lam * dssim_dx
+    return loss, l1, ssim, grad.astype(np.float32)

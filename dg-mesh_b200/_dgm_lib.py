@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("DGMESH_B200_LIB", LIB_PATH)
 
 c_void_p, c_int, c_float, c_size_t, c_int64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t,
                                                ctypes.c_int64)
+c_int32, byref = ctypes.c_int32, ctypes.byref
 P = c_void_p  # every device pointer crosses the boundary as a plain address
 
 # name -> (restype, argtypes); must list every symbol declared in include/dgmesh_b200.h
@@ -22,15 +23,22 @@ SIGNATURES = {
     "dgm_last_error": (ctypes.c_char_p, []),
     "dgr_workspace_sizes": (c_int, [c_int, c_int, c_int, c_int64, ctypes.POINTER(c_size_t),
                                     ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
+    "dgm_notify_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "dgm_notify_host": (c_void_p, [P]),
+    "dgm_notify_event": (c_void_p, [P]),
+    "dgm_notify_wait": (c_int, [P]),
+    "dgm_notify_destroy": (c_int, [P]),
     "dgr_forward": (c_int, [c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_float, P, P, P, P, P,
-                            c_float, c_float, c_int, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P]),
+                            c_float, c_float, c_int, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P, P,
+                            c_float, c_float, P]),
     "dgr_backward": (c_int, [c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P,
                              c_float, c_float, P, P, P, c_int64, P, P, P, P, P, P, P, P, P, P, P, P]),
-    "dgr_forward_batch": (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_float, P, P, P, P, P,
-                                  P, P, c_int, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, c_int, P]),
-    "dgr_backward_batch": (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P,
-                                   P, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P, P, P, P, P, P, P,
-                                   P, c_int, P]),
+    "dgr_forward_batch": (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_float, P, P, c_int,
+                                  P, P, P, P, P, c_int, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P, P,
+                                  c_float, c_float, c_int, P]),
+    "dgr_backward_batch": (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, c_float, P, P, c_int,
+                                   P, P, P, P, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P, P, P, P, P,
+                                   P, P, P, c_int, P]),
     "dgr_mark_visible": (c_int, [c_int, P, P, P, P, P]),
     "dgr_export_state": (c_int, [c_int, c_int, c_int, c_int64, P, P, P] + [P] * 12 + [P]),
     "dgk_workspace_size": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
@@ -78,7 +86,9 @@ class DglNet(ctypes.Structure):
     _fields_ = [("has_timenet", c_int), ("in_t", c_int), ("n_out", c_int), ("sigmoid_out", c_int),
                 ("W", c_void_p * 8), ("WT", c_void_p * 8), ("b", c_void_p * 8),
                 ("Wh", c_void_p), ("WhT", c_void_p), ("bh", c_void_p),
-                ("Wt0", c_void_p), ("bt0", c_void_p), ("Wt1", c_void_p), ("Wt1T", c_void_p), ("bt1", c_void_p)]
+                ("Wt0", c_void_p), ("bt0", c_void_p), ("Wt1", c_void_p), ("Wt1T", c_void_p), ("bt1", c_void_p),
+                ("precise", c_int), ("Wlo", c_void_p * 8), ("Whlo", c_void_p), ("Wt0lo", c_void_p),
+                ("Wt1lo", c_void_p)]
 
 
 class DglRaw(ctypes.Structure):

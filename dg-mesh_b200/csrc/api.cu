@@ -9,6 +9,9 @@
 #include "mlp_kernels.h"
 
 #include <string.h>
+#include <stdlib.h>
+#include <mutex>
+#include <map>
 
 namespace {
 thread_local char g_last_error[256] = "";
@@ -25,6 +28,11 @@ int bad(const char* msg) {
 
 namespace dgm {
 Profiler g_prof;
+// programmatic dependent launch between the rasterizer's kernels (DGMESH_B200_PDL=0 turns it off)
+int g_pdl = [] {
+  const char* e = getenv("DGMESH_B200_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
 // ---- state export (parity tests): rebuild the reference-visible views from the
 // private workspaces.  point_list_keys is reconstructed as (tile << 32 | depth bits),
 // the key the reference sorts on (rasterizer_impl.cu:98-106).
@@ -93,7 +101,8 @@ int dgr_forward(int P, int D, int M, const float* background, int W, int H, cons
                 const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
                 const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, float* out_color, int* radii,
                 void* geom_ws, size_t geom_bytes, void* binning_ws, size_t binning_bytes, int64_t R_cap, void* img_ws,
-                size_t img_bytes, int32_t* status, void* stream) {
+                size_t img_bytes, int32_t* status, int32_t* status_host, void* status_event, float depth_hint_lo,
+                float depth_hint_hi, void* stream) {
   if (P < 0 || W <= 0 || H <= 0 || R_cap < 0) return bad("dgr_forward: negative size");
   if (!background || !viewmatrix || !projmatrix || !cam_pos || !out_color || !status)
     return bad("dgr_forward: null required pointer");
@@ -110,6 +119,8 @@ int dgr_forward(int P, int D, int M, const float* background, int W, int H, cons
     // (rasterize_points.cu:64,80: torch::full(0.0) and `if (P != 0)`)
     cudaMemsetAsync(out_color, 0, sizeof(float) * 3 * (size_t)W * H, (cudaStream_t)stream);
     cudaMemsetAsync(status, 0, sizeof(int32_t) * DGR_STATUS_WORDS, (cudaStream_t)stream);
+    if (status_host) memset(status_host, 0, sizeof(int32_t) * DGR_STATUS_WORDS);
+    if (status_event) cudaEventRecord((cudaEvent_t)status_event, (cudaStream_t)stream);
     return check(cudaGetLastError());
   }
   size_t gb, bb, ib;
@@ -126,6 +137,8 @@ int dgr_forward(int P, int D, int M, const float* background, int W, int H, cons
   a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.prefiltered = prefiltered;
   a.out_color = out_color; a.radii = radii;
   a.geom_ws = geom_ws; a.binning_ws = binning_ws; a.img_ws = img_ws; a.R_cap = R_cap; a.status = status;
+  a.status_host = status_host; a.status_event = (cudaEvent_t)status_event;
+  a.hint_lo = depth_hint_lo; a.hint_hi = depth_hint_hi;
   return check(dgm::launch_forward(a, (cudaStream_t)stream));
 }
 
@@ -170,6 +183,7 @@ struct BatchStreams {
   cudaStream_t hi[NH] = {}, lo[2] = {};
   cudaEvent_t fork = nullptr, done_hi[NH] = {}, done_lo[2] = {}, ready[NH] = {}, blended[2] = {};
   bool ok = false;
+  std::mutex mu;  // one batch call at a time per device (the events above are shared)
   bool init() {
     if (ok) return true;
     int least = 0, greatest = 0;
@@ -189,15 +203,25 @@ struct BatchStreams {
     return true;
   }
 };
-// one set per device would be needed for multi-device processes; this library is used one process per GPU
-BatchStreams g_bs;
+// one set per device, created on first use
+std::mutex g_bs_mu;
+std::map<int, BatchStreams*> g_bs_map;
+BatchStreams* batch_streams() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(g_bs_mu);
+  BatchStreams*& p = g_bs_map[dev];
+  if (!p) p = new BatchStreams();
+  return p->init() ? p : nullptr;
+}
 
 dgm::FwdArgs fwd_args(int P, int D, int M, const float* background, int W, int H, const float* means3D,
                       const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
                       const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
                       float tan_fovy, int prefiltered, float* out_color, int* radii, void* geom_ws, void* binning_ws,
-                      int64_t R_cap, void* img_ws, int32_t* status) {
+                      int64_t R_cap, void* img_ws, int32_t* status, int32_t* status_host, float hint_lo,
+                      float hint_hi) {
   dgm::FwdArgs a;
   a.P = P; a.D = D; a.M = M; a.background = background; a.W = W; a.H = H;
   a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
@@ -206,17 +230,19 @@ dgm::FwdArgs fwd_args(int P, int D, int M, const float* background, int W, int H
   a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.prefiltered = prefiltered;
   a.out_color = out_color; a.radii = radii;
   a.geom_ws = geom_ws; a.binning_ws = binning_ws; a.img_ws = img_ws; a.R_cap = R_cap; a.status = status;
+  a.status_host = status_host; a.status_event = nullptr; a.hint_lo = hint_lo; a.hint_hi = hint_hi;
   return a;
 }
 }  // namespace
 
 int dgr_forward_batch(int F, int P, int D, int M, const float* background, int W, int H, const float* means3D,
                       const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
-                      float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                      float scale_modifier, const float* rotations, const float* cov3D_precomp, int per_frame,
                       const float* viewmatrices, const float* projmatrices, const float* cam_poses,
                       const float* tan_fovx_host, const float* tan_fovy_host, int prefiltered, float* out_color,
                       int* radii, void* geom_ws, size_t geom_stride, void* binning_ws, size_t binning_stride,
-                      int64_t R_cap, void* img_ws, size_t img_stride, int32_t* status, int n_streams, void* stream) {
+                      int64_t R_cap, void* img_ws, size_t img_stride, int32_t* status, int32_t* status_host,
+                      void* status_event, float depth_hint_lo, float depth_hint_hi, int n_streams, void* stream) {
   if (F <= 0 || !tan_fovx_host || !tan_fovy_host || !viewmatrices || !projmatrices || !cam_poses)
     return bad("dgr_forward_batch: bad argument");
   size_t gb, bb, ib;
@@ -228,15 +254,24 @@ int dgr_forward_batch(int F, int P, int D, int M, const float* background, int W
   cudaStream_t main_s = (cudaStream_t)stream;
   const bool multi = n_streams > 1 && F > 1 && P > 0;
   const int NH = multi ? (n_streams > BatchStreams::NH ? BatchStreams::NH : n_streams) : 0;
+  // per-frame inputs (bit set in per_frame) advance by one [P, .] slab per frame
+  auto pf = [&](const float* p, int bit, size_t width, int f) {
+    return (p && (per_frame & bit)) ? p + (size_t)f * P * width : p;
+  };
+  const size_t cw = shs ? (size_t)M * 3 : 3;
   if (!multi) {
     int rc = DGM_OK;
     for (int f = 0; f < F && rc == DGM_OK; ++f)
-      rc = dgr_forward(P, D, M, background, W, H, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
-                       rotations, cov3D_precomp, viewmatrices + 16 * f, projmatrices + 16 * f, cam_poses + 3 * f,
-                       tan_fovx_host[f], tan_fovy_host[f], prefiltered, out_color + (size_t)f * 3 * W * H,
-                       radii ? radii + (size_t)f * P : nullptr, (char*)geom_ws + f * geom_stride, geom_stride,
-                       (char*)binning_ws + f * binning_stride, binning_stride, R_cap, (char*)img_ws + f * img_stride,
-                       img_stride, status + f * DGR_STATUS_WORDS, main_s);
+      rc = dgr_forward(P, D, M, background, W, H, pf(means3D, DGR_PF_MEANS, 3, f), pf(shs, DGR_PF_COLOR, cw, f),
+                       pf(colors_precomp, DGR_PF_COLOR, 3, f), pf(opacities, DGR_PF_OPAC, 1, f),
+                       pf(scales, DGR_PF_SCALES, 3, f), scale_modifier, pf(rotations, DGR_PF_ROTS, 4, f),
+                       pf(cov3D_precomp, DGR_PF_COV, 6, f), viewmatrices + 16 * f, projmatrices + 16 * f,
+                       cam_poses + 3 * f, tan_fovx_host[f], tan_fovy_host[f], prefiltered,
+                       out_color + (size_t)f * 3 * W * H, radii ? radii + (size_t)f * P : nullptr,
+                       (char*)geom_ws + f * geom_stride, geom_stride, (char*)binning_ws + f * binning_stride,
+                       binning_stride, R_cap, (char*)img_ws + f * img_stride, img_stride,
+                       status + f * DGR_STATUS_WORDS, status_host ? status_host + f * DGR_STATUS_WORDS : nullptr,
+                       (f == F - 1) ? status_event : nullptr, depth_hint_lo, depth_hint_hi, main_s);
     return rc;
   }
   if (!background || !out_color || !status || !means3D || !opacities) return bad("dgr_forward_batch: null required pointer");
@@ -245,39 +280,45 @@ int dgr_forward_batch(int F, int P, int D, int M, const float* background, int W
     return bad("dgr_forward_batch: exactly one of scales+rotations / cov3D_precomp");
   if (shs && (M <= 0 || M > 16 || (D + 1) * (D + 1) > M || D < 0 || D > 3))
     return bad("dgr_forward_batch: SH degree / coefficient count");
-  if (!g_bs.init()) return check(cudaGetLastError());
-  cudaEventRecord(g_bs.fork, main_s);
-  for (int i = 0; i < NH; ++i) cudaStreamWaitEvent(g_bs.hi[i], g_bs.fork, 0);
-  for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(g_bs.lo[i], g_bs.fork, 0);
+  BatchStreams* bs = batch_streams();
+  if (!bs) return check(cudaGetLastError());
+  std::lock_guard<std::mutex> lk(bs->mu);
+  cudaEventRecord(bs->fork, main_s);
+  for (int i = 0; i < NH; ++i) cudaStreamWaitEvent(bs->hi[i], bs->fork, 0);
+  for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(bs->lo[i], bs->fork, 0);
   cudaError_t e = cudaSuccess;
   for (int f = 0; f < F && e == cudaSuccess; ++f) {
     const int i = f % NH;
-    cudaStream_t lo = g_bs.lo[f & 1];
+    cudaStream_t lo = bs->lo[f & 1];
     const dgm::FwdArgs a = fwd_args(
-        P, D, M, background, W, H, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
-        cov3D_precomp, viewmatrices + 16 * f, projmatrices + 16 * f, cam_poses + 3 * f, tan_fovx_host[f],
-        tan_fovy_host[f], prefiltered, out_color + (size_t)f * 3 * W * H, radii ? radii + (size_t)f * P : nullptr,
-        (char*)geom_ws + f * geom_stride, (char*)binning_ws + f * binning_stride, R_cap,
-        (char*)img_ws + f * img_stride, status + f * DGR_STATUS_WORDS);
-    e = dgm::launch_binning(a, g_bs.hi[i]);
-    cudaEventRecord(g_bs.ready[i], g_bs.hi[i]);
-    cudaStreamWaitEvent(lo, g_bs.ready[i], 0);
+        P, D, M, background, W, H, pf(means3D, DGR_PF_MEANS, 3, f), pf(shs, DGR_PF_COLOR, cw, f),
+        pf(colors_precomp, DGR_PF_COLOR, 3, f), pf(opacities, DGR_PF_OPAC, 1, f), pf(scales, DGR_PF_SCALES, 3, f),
+        scale_modifier, pf(rotations, DGR_PF_ROTS, 4, f), pf(cov3D_precomp, DGR_PF_COV, 6, f), viewmatrices + 16 * f,
+        projmatrices + 16 * f, cam_poses + 3 * f, tan_fovx_host[f], tan_fovy_host[f], prefiltered,
+        out_color + (size_t)f * 3 * W * H, radii ? radii + (size_t)f * P : nullptr, (char*)geom_ws + f * geom_stride,
+        (char*)binning_ws + f * binning_stride, R_cap, (char*)img_ws + f * img_stride, status + f * DGR_STATUS_WORDS,
+        status_host ? status_host + f * DGR_STATUS_WORDS : nullptr, depth_hint_lo, depth_hint_hi);
+    e = dgm::launch_binning(a, bs->hi[i]);
+    cudaEventRecord(bs->ready[i], bs->hi[i]);
+    cudaStreamWaitEvent(lo, bs->ready[i], 0);
     if (e == cudaSuccess) e = dgm::launch_render(a, lo);
   }
+  // the binning chains finish long before the blend kernels: the caller's status event fires then
   for (int i = 0; i < NH; ++i) {
-    cudaEventRecord(g_bs.done_hi[i], g_bs.hi[i]);
-    cudaStreamWaitEvent(main_s, g_bs.done_hi[i], 0);
+    cudaEventRecord(bs->done_hi[i], bs->hi[i]);
+    cudaStreamWaitEvent(main_s, bs->done_hi[i], 0);
   }
+  if (status_event) cudaEventRecord((cudaEvent_t)status_event, main_s);
   for (int i = 0; i < 2; ++i) {
-    cudaEventRecord(g_bs.done_lo[i], g_bs.lo[i]);
-    cudaStreamWaitEvent(main_s, g_bs.done_lo[i], 0);
+    cudaEventRecord(bs->done_lo[i], bs->lo[i]);
+    cudaStreamWaitEvent(main_s, bs->done_lo[i], 0);
   }
   return check(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 int dgr_backward_batch(int F, int P, int D, int M, const float* background, int W, int H, const float* means3D,
                        const float* shs, const float* colors_precomp, const float* scales, float scale_modifier,
-                       const float* rotations, const float* cov3D_precomp, const float* viewmatrices,
+                       const float* rotations, const float* cov3D_precomp, int per_frame, const float* viewmatrices,
                        const float* projmatrices, const float* cam_poses, const float* tan_fovx_host,
                        const float* tan_fovy_host, const int* radii, void* geom_ws, size_t geom_stride,
                        void* binning_ws, size_t binning_stride, int64_t R_cap, void* img_ws, size_t img_stride,
@@ -296,19 +337,32 @@ int dgr_backward_batch(int F, int P, int D, int M, const float* background, int 
   const bool multi = n_streams > 1 && F > 1;
   cudaStream_t main_s = (cudaStream_t)stream;
   cudaStream_t s_pp = main_s;
+  BatchStreams* bs = nullptr;
+  std::unique_lock<std::mutex> lk;
   if (multi) {
-    if (!g_bs.init()) return check(cudaGetLastError());
-    s_pp = g_bs.hi[0];
-    cudaEventRecord(g_bs.fork, main_s);
-    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(g_bs.lo[i], g_bs.fork, 0);
-    cudaStreamWaitEvent(s_pp, g_bs.fork, 0);
+    bs = batch_streams();
+    if (!bs) return check(cudaGetLastError());
+    lk = std::unique_lock<std::mutex>(bs->mu);
+    s_pp = bs->hi[0];
+    cudaEventRecord(bs->fork, main_s);
+    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(bs->lo[i], bs->fork, 0);
+    cudaStreamWaitEvent(s_pp, bs->fork, 0);
   }
+  auto pf = [&](const float* p, int bit, size_t width, int f) {
+    return (p && (per_frame & bit)) ? p + (size_t)f * P * width : p;
+  };
+  auto pfo = [&](float* p, int bit, size_t width, int f) {
+    return (p && (per_frame & bit)) ? p + (size_t)f * P * width : p;
+  };
+  const size_t cw = shs ? (size_t)M * 3 : 3;
   cudaError_t e = cudaSuccess;
   for (int f = 0; f < F && e == cudaSuccess; ++f) {
     dgm::BwdArgs a;
     a.P = P; a.D = D; a.M = M; a.background = background; a.W = W; a.H = H;
-    a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales;
-    a.scale_modifier = scale_modifier; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+    a.means3D = pf(means3D, DGR_PF_MEANS, 3, f); a.shs = pf(shs, DGR_PF_COLOR, cw, f);
+    a.colors_precomp = pf(colors_precomp, DGR_PF_COLOR, 3, f); a.scales = pf(scales, DGR_PF_SCALES, 3, f);
+    a.scale_modifier = scale_modifier; a.rotations = pf(rotations, DGR_PF_ROTS, 4, f);
+    a.cov3D_precomp = pf(cov3D_precomp, DGR_PF_COV, 6, f);
     a.viewmatrix = viewmatrices + 16 * f; a.projmatrix = projmatrices + 16 * f; a.cam_pos = cam_poses + 3 * f;
     a.tan_fovx = tan_fovx_host[f]; a.tan_fovy = tan_fovy_host[f];
     a.radii = radii ? radii + (size_t)f * P : nullptr;
@@ -316,24 +370,28 @@ int dgr_backward_batch(int F, int P, int D, int M, const float* background, int 
     a.img_ws = (char*)img_ws + f * img_stride; a.R_cap = R_cap;
     a.dL_dpix = dL_dpix + (size_t)f * 3 * W * H;
     a.dL_dmean2D = dL_dmean2D + (size_t)f * P * 3; a.dL_dconic = nullptr;
-    a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D;
-    a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
-    a.accumulate = f > 0;
-    cudaStream_t s_blend = multi ? g_bs.lo[f & 1] : main_s;
+    a.dL_dopacity = pfo(dL_dopacity, DGR_PF_OPAC, 1, f);
+    a.dL_dcolor = pfo(dL_dcolor, shs ? 0 : DGR_PF_COLOR, 3, f);  // with SH colours dL_dcolor is scratch
+    a.dL_dmean3D = pfo(dL_dmean3D, DGR_PF_MEANS, 3, f); a.dL_dcov3D = pfo(dL_dcov3D, DGR_PF_COV, 6, f);
+    a.dL_dsh = pfo(dL_dsh, DGR_PF_COLOR, cw, f); a.dL_dscale = pfo(dL_dscale, DGR_PF_SCALES, 3, f);
+    a.dL_drot = pfo(dL_drot, DGR_PF_ROTS, 4, f);
+    // shared inputs: the first frame writes, later frames add; per-frame inputs: always written
+    a.accumulate = (f > 0) ? (DGR_PF_ALL & ~per_frame) : 0;
+    cudaStream_t s_blend = multi ? bs->lo[f & 1] : main_s;
     e = dgm::launch_render_bwd(a, s_blend);
     if (multi) {
-      cudaEventRecord(g_bs.blended[f & 1], s_blend);
-      cudaStreamWaitEvent(s_pp, g_bs.blended[f & 1], 0);
+      cudaEventRecord(bs->blended[f & 1], s_blend);
+      cudaStreamWaitEvent(s_pp, bs->blended[f & 1], 0);
     }
     if (e == cudaSuccess) e = dgm::launch_preprocess_bwd(a, s_pp);
   }
   if (multi) {
     for (int i = 0; i < 2; ++i) {
-      cudaEventRecord(g_bs.done_lo[i], g_bs.lo[i]);
-      cudaStreamWaitEvent(main_s, g_bs.done_lo[i], 0);
+      cudaEventRecord(bs->done_lo[i], bs->lo[i]);
+      cudaStreamWaitEvent(main_s, bs->done_lo[i], 0);
     }
-    cudaEventRecord(g_bs.done_hi[0], s_pp);
-    cudaStreamWaitEvent(main_s, g_bs.done_hi[0], 0);
+    cudaEventRecord(bs->done_hi[0], s_pp);
+    cudaStreamWaitEvent(main_s, bs->done_hi[0], 0);
   }
   return check(e != cudaSuccess ? e : cudaGetLastError());
 }
@@ -525,6 +583,11 @@ static int dgl_check(const DglNet* n, int P, const void* ws, size_t ws_bytes, in
   for (int l = 0; l < 8; ++l)
     if (!n->W[l] || !n->b[l]) return bad("mlp: missing layer");
   if (n->has_timenet && (!n->Wt0 || !n->bt0 || !n->Wt1 || !n->bt1)) return bad("mlp: missing timenet");
+  if (n->precise) {
+    for (int l = 0; l < 8; ++l)
+      if (!n->Wlo[l]) return bad("mlp: precise forward without residual operands");
+    if (!n->Whlo || (n->has_timenet && (!n->Wt0lo || !n->Wt1lo))) return bad("mlp: precise forward without residual operands");
+  }
   if (ws_bytes < dgm::mlp_workspace_bytes(P, train)) {
     strncpy(g_last_error, "mlp: workspace too small", sizeof(g_last_error) - 1);
     return DGM_E_WORKSPACE;
@@ -577,6 +640,41 @@ int dgloss_backward(int H, int W, const float* img, const float* gt, float lambd
     return DGM_E_WORKSPACE;
   }
   return check(dgm::launch_loss_backward(H, W, img, gt, lambda_dssim, mode, dL_dloss, dL_dimg, ws, (cudaStream_t)stream));
+}
+
+// ---- early notification objects: an event + a device-mapped pinned status mirror.  These are the
+// only resources the library creates on request (host memory and an event, no device memory).
+struct DgmNotify {
+  cudaEvent_t ev;
+  int32_t* host;
+};
+
+int dgm_notify_create(void** handle) {
+  if (!handle) return bad("dgm_notify_create: null handle");
+  DgmNotify* n = new DgmNotify();
+  if (cudaEventCreateWithFlags(&n->ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaHostAlloc((void**)&n->host, sizeof(int32_t) * DGR_STATUS_WORDS * 64,
+                    cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    delete n;
+    return check(cudaGetLastError());
+  }
+  memset(n->host, 0, sizeof(int32_t) * DGR_STATUS_WORDS * 64);
+  *handle = n;
+  return DGM_OK;
+}
+int32_t* dgm_notify_host(void* handle) { return handle ? ((DgmNotify*)handle)->host : nullptr; }
+void* dgm_notify_event(void* handle) { return handle ? (void*)((DgmNotify*)handle)->ev : nullptr; }
+int dgm_notify_wait(void* handle) {
+  if (!handle) return bad("dgm_notify_wait: null handle");
+  return check(cudaEventSynchronize(((DgmNotify*)handle)->ev));
+}
+int dgm_notify_destroy(void* handle) {
+  if (!handle) return DGM_OK;
+  DgmNotify* n = (DgmNotify*)handle;
+  cudaEventDestroy(n->ev);
+  cudaFreeHost(n->host);
+  delete n;
+  return DGM_OK;
 }
 
 int dgm_profile_enable(int on) {

@@ -143,10 +143,39 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ------------------------------------------- programmatic dependent launch ----
+// A kernel launched with launch_pdl() may become resident while its predecessor on the stream is
+// still running; it must call pdl_wait() before reading anything the predecessor wrote (the wait
+// returns once the predecessor grid has completed and its memory is visible).  pdl_launch() lets
+// the NEXT kernel's CTAs be scheduled as this grid's last wave drains.  Both are no-ops for a
+// kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // vector float reductions to global memory (sm_90+): one L2 atomic transaction for 4 floats
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
+
+
+#ifdef __CUDACC__
+// host: launch `k` with the programmatic-stream-serialization attribute (pdl != 0) or plainly
+extern int g_pdl;  // api.cu; DGMESH_B200_PDL=0 disables
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
+}
+#endif
 
 }  // namespace dgm

@@ -64,6 +64,8 @@ struct MlpBufs {
   __nv_bfloat16 *dZ[2], *dZh, *dZt1;
   uint32_t *M[8], *Mt1;                 // ReLU masks as bits, [tiles][8][128] words (training only)
   float* dE;                            // [Pp, 96] fp32 row-major: gradient w.r.t. the embedded inputs
+  // split-precision forward: rounding residuals of A5 / T0 / T1 and of the running hidden activation
+  __nv_bfloat16 *A5lo, *T0lo, *T1lo, *Hlo[2];
   int Pp, tiles;
   static MlpBufs carve_all(char* base, int P, int train, size_t* bytes) {
     char* p = base;
@@ -74,6 +76,11 @@ struct MlpBufs {
     b.A5 = carve<__nv_bfloat16>(p, Pp * K5);
     b.T0 = carve<__nv_bfloat16>(p, Pp * 16);
     b.T1 = carve<__nv_bfloat16>(p, Pp * WID);
+    b.A5lo = carve<__nv_bfloat16>(p, Pp * K5);
+    b.T0lo = carve<__nv_bfloat16>(p, Pp * 16);
+    b.T1lo = carve<__nv_bfloat16>(p, Pp * WID);
+    b.Hlo[0] = carve<__nv_bfloat16>(p, Pp * WID);
+    b.Hlo[1] = carve<__nv_bfloat16>(p, Pp * WID);
     if (train) {
       for (int l = 0; l < 8; ++l) b.H[l] = (l == 4) ? b.A5 : carve<__nv_bfloat16>(p, Pp * WID);
       for (int i = 0; i < 2; ++i) b.dZ[i] = carve<__nv_bfloat16>(p, Pp * WID);
@@ -99,6 +106,8 @@ struct MlpBufs {
     return (l == 4) ? BlkView{A5, (size_t)K5 * ACT_R, K0 / 8} : BlkView{H[l], (size_t)WID * ACT_R, 0};
   }
   BlkView a5() const { return BlkView{A5, (size_t)K5 * ACT_R, 0}; }
+  // residual buffer with the geometry of h(l): layer l's output residual / layer l+1's input residual
+  __nv_bfloat16* hlo(int l) const { return (l == 4) ? A5lo : Hlo[l & 1]; }
 };
 
 __device__ __forceinline__ uint4 pack8(const float* v) {
@@ -115,9 +124,18 @@ __device__ __forceinline__ uint4* blk_unit(__nv_bfloat16* base, int F, int row, 
 
 // positional encodings (time_utils.py:8-55): [v, sin(v 2^0), cos(v 2^0), ..., sin(v 2^(L-1)), cos(v 2^(L-1))]
 // One thread per row (padding rows get zeros); writes the x block (+ direct time features) of A5 and T0.
+// residuals of pack8(v): lo[i] = bf16(v[i] - float(bf16(v[i])))
+__device__ __forceinline__ uint4 pack8_lo(const float* v) {
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+  return pack8(r);
+}
+
 __global__ void __launch_bounds__(256) pe_kernel(int P, int Pp, const float* __restrict__ x,
                                                  const float* __restrict__ t, int has_timenet, int t_freqs,
-                                                 __nv_bfloat16* __restrict__ A5, __nv_bfloat16* __restrict__ T0) {
+                                                 __nv_bfloat16* __restrict__ A5, __nv_bfloat16* __restrict__ T0,
+                                                 __nv_bfloat16* __restrict__ A5lo, __nv_bfloat16* __restrict__ T0lo) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Pp) return;
   const bool ok = p < P;
@@ -158,10 +176,17 @@ __global__ void __launch_bounds__(256) pe_kernel(int P, int Pp, const float* __r
   const int nkb = has_timenet ? TCOL / 8 : K0 / 8;  // with a timenet its GEMM writes kbs 8..11
 #pragma unroll
   for (int kb = 0; kb < K0 / 8; ++kb)
-    if (kb < nkb) *blk_unit(A5, K5, p, kb) = pack8(e + 8 * kb);
+    if (kb < nkb) {
+      *blk_unit(A5, K5, p, kb) = pack8(e + 8 * kb);
+      if (A5lo) *blk_unit(A5lo, K5, p, kb) = pack8_lo(e + 8 * kb);
+    }
   if (has_timenet) {
     *blk_unit(T0, 16, p, 0) = pack8(te);
     *blk_unit(T0, 16, p, 1) = pack8(te + 8);
+    if (T0lo) {
+      *blk_unit(T0lo, 16, p, 0) = pack8_lo(te);
+      *blk_unit(T0lo, 16, p, 1) = pack8_lo(te + 8);
+    }
   }
 }
 
@@ -277,14 +302,18 @@ cudaError_t launch_mlp_forward(const DglNet& n, int P, const float* x, const flo
                                void* ws, cudaStream_t s) {
   MlpBufs b = MlpBufs::carve_all((char*)ws, P, train, nullptr);
   const int Pp = b.Pp, tiles = b.tiles;
-  pe_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(P, Pp, x, t, n.has_timenet, n.has_timenet ? 6 : 10, b.A5, b.T0);
+  const bool hp = n.precise != 0;  // split-precision forward (bf16x3)
+  pe_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(P, Pp, x, t, n.has_timenet, n.has_timenet ? 6 : 10, b.A5, b.T0,
+                                             hp ? b.A5lo : nullptr, hp ? b.T0lo : nullptr);
   if (n.has_timenet) {
     LayerArgs g = layer(BlkView{b.T0, (size_t)16 * ACT_R, 0}, 16, (CB)n.Wt0, WID, tiles);
     g.bias = n.bt0; g.relu = 1; g.out = b.T1; g.out_tile_stride = (size_t)WID * ACT_R;
     g.mask_out = b.Mt1;
+    if (hp) { g.A_lo = b.T0lo; g.B_lo = (CB)n.Wt0lo; g.out_lo = b.T1lo; }
     CK(launch_layer_gemm(g, s));
     g = layer(BlkView{b.T1, (size_t)WID * ACT_R, 0}, WID, (CB)n.Wt1, 32, tiles);  // 30 outputs padded to 32
     g.bias = n.bt1; g.out = b.A5; g.out_tile_stride = (size_t)K5 * ACT_R; g.out_kb0 = TCOL / 8;
+    if (hp) { g.A_lo = b.T1lo; g.B_lo = (CB)n.Wt1lo; g.out_lo = b.A5lo; }
     CK(launch_layer_gemm(g, s));
   }
   for (int l = 0; l < 8; ++l) {
@@ -295,10 +324,16 @@ cudaError_t launch_mlp_forward(const DglNet& n, int P, const float* x, const flo
     const BlkView o = b.h(l);
     g.out = const_cast<__nv_bfloat16*>(o.p); g.out_tile_stride = o.tile_stride; g.out_kb0 = o.kb0;
     g.mask_out = b.M[l];
+    if (hp) {
+      g.A_lo = (l == 0 || l == 5) ? b.A5lo : b.hlo(l - 1);
+      g.B_lo = (CB)n.Wlo[l];
+      g.out_lo = b.hlo(l);
+    }
     CK(launch_layer_gemm(g, s));
   }
   LayerArgs g = layer(b.h(7), WID, (CB)n.Wh, 16, tiles);
   g.bias = n.bh; g.out_f32 = out; g.ld_f32 = 16; g.n_f32 = 16; g.rows_valid = P;
+  if (hp) { g.A_lo = b.hlo(7); g.B_lo = (CB)n.Whlo; }
   CK(launch_layer_gemm(g, s));
   if (n.sigmoid_out) sigmoid_kernel<<<(P * 16 + 255) / 256, 256, 0, s>>>(P * 16, out);
   return cudaGetLastError();
@@ -482,6 +517,7 @@ struct PackEntry {
   const float* src;          // pack: raw weight / bias;  unpack: packed fp32 gradient
   float* dst_f32;            // bias copy / unpacked gradient
   __nv_bfloat16 *dst, *dstT, *dstT_e;
+  __nv_bfloat16* dst_lo;     // forward operand of the split-precision path: bf16(w - float(bf16(w)))
   int rows, kin, mapped, r0, Rf, Rt, kpad, is_bias;
 };
 #define PACK_MAX 32
@@ -502,6 +538,8 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackTable t) {
     const int cc = map_col(c, t.in_t, E.mapped), o = E.r0 + r;
     const __nv_bfloat16 v = __float2bfloat16_rn(E.src[i]);
     E.dst[((size_t)(cc >> 3) * E.Rf + o) * 8 + (cc & 7)] = v;
+    if (E.dst_lo)
+      E.dst_lo[((size_t)(cc >> 3) * E.Rf + o) * 8 + (cc & 7)] = __float2bfloat16_rn(E.src[i] - __bfloat162float(v));
     if (E.mapped) {
       if (cc < K0) {
         if (E.dstT_e) E.dstT_e[((size_t)(o >> 3) * K0 + cc) * 8 + (o & 7)] = v;
@@ -530,6 +568,7 @@ __global__ void __launch_bounds__(256) unpack_all_kernel(const PackTable t) {
 // fixed layout of the packed buffers (elements)
 struct PackLayout {
   size_t W[8], WT[8], Wh, WhT, Wt0, Wt1, Wt1T, w_total;  // bf16 elements
+  size_t Wlo[8], Whlo, Wt0lo, Wt1lo;                      // residual forward operands (split precision)
   size_t b[8], bh, bt0, bt1, b_total;                     // fp32 elements
   // gradient buffer (fp32 elements): same matrices, no transposes
   size_t gW[8], gb[8], gWh, gbh, gWt0, gbt0, gWt1, gbt1, g_total;
@@ -543,6 +582,8 @@ struct PackLayout {
     }
     Wh = take(16 * WID); WhT = take(16 * WID);
     Wt0 = take(WID * 16); Wt1 = take(32 * WID); Wt1T = take(32 * WID);
+    for (int l = 0; l < 8; ++l) Wlo[l] = take(WID * ((l == 0) ? K0 : (l == 5 ? K5 : WID)));
+    Whlo = take(16 * WID); Wt0lo = take(WID * 16); Wt1lo = take(32 * WID);
     w_total = o;
     o = 0;
     for (int l = 0; l < 8; ++l) b[l] = take(WID);
@@ -584,10 +625,10 @@ cudaError_t launch_mlp_pack(const DglRaw& r, void* wbuf, float* bbuf, DglNet* ne
   PackTable T = {};
   T.in_t = r.in_t;
   auto pack = [&](const float* src, int rows, int kin, int mapped, int r0, int Rf, size_t dst, size_t dstT, int Rt,
-                  size_t dstT_e) {
+                  size_t dstT_e, size_t dst_lo) {
     PackEntry& E = T.e[T.n++];
     E.src = src; E.rows = rows; E.kin = kin; E.mapped = mapped; E.r0 = r0; E.Rf = Rf;
-    E.dst = w + dst; E.dstT = at(dstT); E.Rt = Rt; E.dstT_e = at(dstT_e);
+    E.dst = w + dst; E.dstT = at(dstT); E.Rt = Rt; E.dstT_e = at(dstT_e); E.dst_lo = w + dst_lo;
   };
   auto bias = [&](const float* src, int n_el, float* dst) {
     PackEntry& E = T.e[T.n++];
@@ -596,23 +637,26 @@ cudaError_t launch_mlp_pack(const DglRaw& r, void* wbuf, float* bbuf, DglNet* ne
   for (int l = 0; l < 8; ++l) {
     const int kin = (l == 0) ? in_width(r) : (l == 5 ? in_width(r) + WID : WID);
     // WT[0] holds only the [x_emb, t] block; WT[5] the hidden block followed by the [x_emb, t] block
-    if (l == 0) pack(r.W[l], WID, kin, 1, 0, WID, L.W[l], NONE, 0, L.WT[l]);
-    else if (l == 5) pack(r.W[l], WID, kin, 1, 0, WID, L.W[l], L.WT[l], WID, L.WT[l] + (size_t)WID * WID);
-    else pack(r.W[l], WID, kin, 0, 0, WID, L.W[l], L.WT[l], WID, NONE);
+    if (l == 0) pack(r.W[l], WID, kin, 1, 0, WID, L.W[l], NONE, 0, L.WT[l], L.Wlo[l]);
+    else if (l == 5) pack(r.W[l], WID, kin, 1, 0, WID, L.W[l], L.WT[l], WID, L.WT[l] + (size_t)WID * WID, L.Wlo[l]);
+    else pack(r.W[l], WID, kin, 0, 0, WID, L.W[l], L.WT[l], WID, NONE, L.Wlo[l]);
     bias(r.b[l], WID, bbuf + L.b[l]);
     net->W[l] = w + L.W[l]; net->WT[l] = w + L.WT[l]; net->b[l] = bbuf + L.b[l];
+    net->Wlo[l] = w + L.Wlo[l];
   }
   int r0 = 0;
   for (int h = 0; h < r.n_heads; ++h) {
-    pack(r.Wh[h], r.head_rows[h], WID, 0, r0, 16, L.Wh, L.WhT, WID, NONE);
+    pack(r.Wh[h], r.head_rows[h], WID, 0, r0, 16, L.Wh, L.WhT, WID, NONE, L.Whlo);
     bias(r.bh[h], r.head_rows[h], bbuf + L.bh + r0);
     r0 += r.head_rows[h];
   }
   net->n_out = r0;
   net->Wh = w + L.Wh; net->WhT = w + L.WhT; net->bh = bbuf + L.bh;
+  net->Whlo = w + L.Whlo; net->Wt0lo = w + L.Wt0lo; net->Wt1lo = w + L.Wt1lo;
+  net->precise = 1;  // the caller may clear it to run the single-pass bf16 forward
   if (r.has_timenet) {
-    pack(r.Wt0, WID, 13, 0, 0, WID, L.Wt0, NONE, 0, NONE);
-    pack(r.Wt1, r.in_t, WID, 0, 0, 32, L.Wt1, L.Wt1T, WID, NONE);
+    pack(r.Wt0, WID, 13, 0, 0, WID, L.Wt0, NONE, 0, NONE, L.Wt0lo);
+    pack(r.Wt1, r.in_t, WID, 0, 0, 32, L.Wt1, L.Wt1T, WID, NONE, L.Wt1lo);
     bias(r.bt0, WID, bbuf + L.bt0);
     bias(r.bt1, r.in_t, bbuf + L.bt1);
     net->Wt0 = w + L.Wt0; net->Wt1 = w + L.Wt1; net->Wt1T = w + L.Wt1T;

@@ -53,6 +53,13 @@ struct LayerArgs {
   int out_kb0;
   float* out_f32;             // row-major [rows, ld_f32] or null; first n_f32 columns
   int ld_f32, n_f32, atomic;  // atomic: accumulate with red.global.add
+  // split precision ("bf16x3"): operands are pairs hi + lo of bf16 numbers (lo = the rounding
+  // residual of hi), the product is A_hi B_hi + A_lo B_hi + A_hi B_lo accumulated in fp32 -- three
+  // passes over K into the same TMEM accumulator, ~16 mantissa bits per operand.  A_lo / B_lo have
+  // the geometry of A / B; out_lo (optional) receives the residual of the bf16 output.
+  const __nv_bfloat16* A_lo;  // null: single pass
+  const __nv_bfloat16* B_lo;
+  __nv_bfloat16* out_lo;
 };
 
 #define LG_STAGES 4
@@ -93,6 +100,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
 
   const int nkb = g.K >> 3;            // 8-wide k blocks
   const int nchunks = (nkb + 7) >> 3;  // K chunks of (up to) 64
+  const int npasses = g.A_lo ? 3 : 1;
   const int my_tiles = (g.tiles > (int)blockIdx.x) ? (g.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
@@ -101,15 +109,20 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
       uint32_t it = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
-        const __nv_bfloat16* a_tile = g.A.p + (size_t)tile * g.A.tile_stride + (size_t)g.A.kb0 * KB_ELEMS;
-        for (int c = 0; c < nchunks; ++c, ++it) {
-          const int st = it % LG_STAGES;
-          const int kbs = min(8, nkb - 8 * c);
-          mbar_wait(&s_empty[st], ((it / LG_STAGES) & 1) ^ 1);
-          const uint32_t a_bytes = kbs * (ACT_R * 16), b_bytes = kbs * g.N * 16;
-          mbar_expect_tx(&s_full[st], a_bytes + b_bytes);
-          tma_load_1d_u32(sA + st * LG_A_BYTES, a_tile + (size_t)c * 8 * KB_ELEMS, a_bytes, &s_full[st]);
-          tma_load_1d_u32(sB + st * LG_B_BYTES, g.B + (size_t)c * 8 * g.N * 8, b_bytes, &s_full[st]);
+        const size_t a_off = (size_t)tile * g.A.tile_stride + (size_t)g.A.kb0 * KB_ELEMS;
+        for (int pass = 0; pass < npasses; ++pass) {
+          // pass 0: A_hi B_hi, pass 1: A_lo B_hi, pass 2: A_hi B_lo
+          const __nv_bfloat16* a_tile = ((pass == 1) ? g.A_lo : g.A.p) + a_off;
+          const __nv_bfloat16* b_mat = (pass == 2) ? g.B_lo : g.B;
+          for (int c = 0; c < nchunks; ++c, ++it) {
+            const int st = it % LG_STAGES;
+            const int kbs = min(8, nkb - 8 * c);
+            mbar_wait(&s_empty[st], ((it / LG_STAGES) & 1) ^ 1);
+            const uint32_t a_bytes = kbs * (ACT_R * 16), b_bytes = kbs * g.N * 16;
+            mbar_expect_tx(&s_full[st], a_bytes + b_bytes);
+            tma_load_1d_u32(sA + st * LG_A_BYTES, a_tile + (size_t)c * 8 * KB_ELEMS, a_bytes, &s_full[st]);
+            tma_load_1d_u32(sB + st * LG_B_BYTES, b_mat + (size_t)c * 8 * g.N * 8, b_bytes, &s_full[st]);
+          }
         }
       }
     }
@@ -124,7 +137,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
         mbar_wait(&s_acc_empty[buf], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         umma::fence_after_sync();
         const uint32_t d_tmem = tmem + buf * 256;
-        for (int c = 0; c < nchunks; ++c, ++it) {
+        for (int pc = 0; pc < npasses * nchunks; ++pc, ++it) {
+          const int c = pc % nchunks;
           const int st = it % LG_STAGES;
           const int kbs = min(8, nkb - 8 * c);
           mbar_wait(&s_full[st], (it / LG_STAGES) & 1);
@@ -132,7 +146,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
           for (int ks = 0; ks < (kbs >> 1); ++ks) {
             const uint64_t da = umma::smem_desc(sA + st * LG_A_BYTES + ks * 2 * (ACT_R * 16), ACT_R * 16, 128);
             const uint64_t db = umma::smem_desc(sB + st * LG_B_BYTES + ks * 2 * lbo_b, lbo_b, 128);
-            umma::mma_bf16(d_tmem, da, db, idesc, (c | ks) != 0);
+            umma::mma_bf16(d_tmem, da, db, idesc, (pc | ks) != 0);
           }
           umma::commit(&s_empty[st]);  // the stage is reusable once these MMAs have read it
         }
@@ -185,6 +199,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
           const int nunits = min(4, (g.N - c0) >> 3);  // 8-column units of this 32-column slice
           if (g.out) {
             __nv_bfloat16* ot = g.out + (size_t)tile * g.out_tile_stride;
+            __nv_bfloat16* ol = g.out_lo ? g.out_lo + (size_t)tile * g.out_tile_stride : nullptr;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (u < nunits) {
@@ -192,7 +207,18 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
                 __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) p2[k] = __floats2bfloat162_rn(v[8 * u + 2 * k], v[8 * u + 2 * k + 1]);
-                *reinterpret_cast<uint4*>(ot + ((size_t)(g.out_kb0 + (c0 >> 3) + u) * ACT_R + r) * 8) = pk;
+                const size_t off = ((size_t)(g.out_kb0 + (c0 >> 3) + u) * ACT_R + r) * 8;
+                *reinterpret_cast<uint4*>(ot + off) = pk;
+                if (ol) {  // uniform: the rounding residual as a second bf16 number
+                  uint4 pl;
+                  __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&pl);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 hi = __bfloat1622float2(p2[k]);
+                    l2[k] = __floats2bfloat162_rn(v[8 * u + 2 * k] - hi.x, v[8 * u + 2 * k + 1] - hi.y);
+                  }
+                  *reinterpret_cast<uint4*>(ol + off) = pl;
+                }
               }
             }
           }

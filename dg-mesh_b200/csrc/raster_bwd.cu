@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(256, 4) render_bwd_kernel(
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ int s_maxc;
 
+  pdl_wait();
+  pdl_launch();
   const unsigned gx = (W + TILE_X - 1) / TILE_X;
   const unsigned tile = tile_order[blockIdx.x];  // longest lists first
   const unsigned tx = tile % gx, ty = tile / gx;
@@ -386,6 +388,15 @@ __device__ __forceinline__ float3 sh_backward(int deg, const float3 pos, const f
 // write v, or add it to what the buffer holds (never reads the buffer unless accumulating)
 __device__ __forceinline__ void acc_store(float* p, float v, int accumulate) { *p = accumulate ? *p + v : v; }
 
+// `accumulate` bits (DGR_PF_* of include/dgmesh_b200.h): which parameter-gradient outputs are summed
+#define ACC_MEANS 1
+#define ACC_SCALES 2
+#define ACC_ROTS 4
+#define ACC_OPAC 8
+#define ACC_COLOR 16  // dL_dsh / dL_dcolor
+#define ACC_COV 32
+#define ACC_ALL 63
+
 __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
     int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
     const float* __restrict__ shs, const float* __restrict__ scales, const float* __restrict__ rotations,
@@ -395,6 +406,8 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D,
     float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscale,
     float* __restrict__ dL_drot, int accumulate) {
+  pdl_wait();
+  pdl_launch();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
   const bool visible = radii[idx] > 0;
@@ -413,11 +426,11 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
   dL_dmean2D[3 * idx + 2] = 0.f;
   if (dL_dconic) reinterpret_cast<float4*>(dL_dconic)[idx] = make_float4(dcon.x, dcon.y, 0.f, dcon.z);
   // parameter gradients: written, or (frame batches) added to the running sum over frames
-  if (accumulate && !visible) return;  // a culled Gaussian adds nothing
-  acc_store(&dL_dopacity[idx], dop, accumulate);
-  acc_store(&dL_dcolor[3 * idx + 0], dcol.x, accumulate);
-  acc_store(&dL_dcolor[3 * idx + 1], dcol.y, accumulate);
-  acc_store(&dL_dcolor[3 * idx + 2], dcol.z, accumulate);
+  if (accumulate == ACC_ALL && !visible) return;  // a culled Gaussian adds nothing
+  acc_store(&dL_dopacity[idx], dop, accumulate & ACC_OPAC);
+  acc_store(&dL_dcolor[3 * idx + 0], dcol.x, accumulate & ACC_COLOR);
+  acc_store(&dL_dcolor[3 * idx + 1], dcol.y, accumulate & ACC_COLOR);
+  acc_store(&dL_dcolor[3 * idx + 2], dcol.z, accumulate & ACC_COLOR);
 
   float dcov[6] = {0, 0, 0, 0, 0, 0};
   float3 dmean = make_float3(0, 0, 0);
@@ -425,7 +438,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
   float4 drot = make_float4(0, 0, 0, 0);
 
   if (!visible) {
-    if (dL_dsh) {
+    if (dL_dsh && !(accumulate & ACC_COLOR)) {
       float* dst = dL_dsh + (size_t)idx * M * 3;
       if (M == 16) {
 #pragma unroll
@@ -517,7 +530,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
           float4 o = make_float4(dsh[4 * i], dsh[4 * i + 1], dsh[4 * i + 2], dsh[4 * i + 3]);
-          if (accumulate) {
+          if (accumulate & ACC_COLOR) {
             const float4 old = reinterpret_cast<float4*>(dst)[i];
             o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
           }
@@ -526,7 +539,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
       } else {
 #pragma unroll
         for (int i = 0; i < 48; ++i)
-          if (i < M * 3) acc_store(&dst[i], dsh[i], accumulate);
+          if (i < M * 3) acc_store(&dst[i], dsh[i], accumulate & ACC_COLOR);
       }
     }
     // ---------------- 3D covariance -> scale / rotation (backward.cu:279-341)
@@ -583,17 +596,17 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(
                2 * y * (dMt.c[1][2] + dMt.c[2][1]) - 4 * z * (dMt.c[1][1] + dMt.c[0][0]);
     }
   }
-  acc_store(&dL_dmean3D[3 * idx + 0], dmean.x, accumulate);
-  acc_store(&dL_dmean3D[3 * idx + 1], dmean.y, accumulate);
-  acc_store(&dL_dmean3D[3 * idx + 2], dmean.z, accumulate);
+  acc_store(&dL_dmean3D[3 * idx + 0], dmean.x, accumulate & ACC_MEANS);
+  acc_store(&dL_dmean3D[3 * idx + 1], dmean.y, accumulate & ACC_MEANS);
+  acc_store(&dL_dmean3D[3 * idx + 2], dmean.z, accumulate & ACC_MEANS);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) acc_store(&dL_dcov3D[6 * idx + k], dcov[k], accumulate);
-  acc_store(&dL_dscale[3 * idx + 0], dscale.x, accumulate);
-  acc_store(&dL_dscale[3 * idx + 1], dscale.y, accumulate);
-  acc_store(&dL_dscale[3 * idx + 2], dscale.z, accumulate);
+  for (int k = 0; k < 6; ++k) acc_store(&dL_dcov3D[6 * idx + k], dcov[k], accumulate & ACC_COV);
+  acc_store(&dL_dscale[3 * idx + 0], dscale.x, accumulate & ACC_SCALES);
+  acc_store(&dL_dscale[3 * idx + 1], dscale.y, accumulate & ACC_SCALES);
+  acc_store(&dL_dscale[3 * idx + 2], dscale.z, accumulate & ACC_SCALES);
   {
     float4 o = drot;
-    if (accumulate) {
+    if (accumulate & ACC_ROTS) {
       const float4 old = reinterpret_cast<float4*>(dL_drot)[idx];
       o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
     }
@@ -615,8 +628,9 @@ cudaError_t launch_render_bwd(const BwdArgs& a, cudaStream_t s) {
   ImgWS im = ImgWS::from((char*)a.img_ws, (size_t)a.W * a.H, T);
   BinWS b = BinWS::from((char*)a.binning_ws, (size_t)a.R_cap);
   g_prof.begin(5, s);
-  render_bwd_kernel<<<T, 256, 0, s>>>(im.ranges, im.tile_order, b.inst_geo, b.inst_attr, a.W, a.H, a.background,
-                                      im.final_T, im.n_contrib, a.dL_dpix, g.grad_acc);
+  launch_pdl(render_bwd_kernel, dim3(T), dim3(256), 0, s, (const uint2*)im.ranges, (const uint32_t*)im.tile_order,
+             (const float4*)b.inst_geo, (const float4*)b.inst_attr, a.W, a.H, a.background, (const float*)im.final_T,
+             (const uint32_t*)im.n_contrib, a.dL_dpix, g.grad_acc);
   g_prof.end(5, s);
   return cudaGetLastError();
 }
@@ -630,10 +644,10 @@ cudaError_t launch_preprocess_bwd(const BwdArgs& a, cudaStream_t s) {
   const float focal_x = a.W / (2.0f * a.tan_fovx);
   const int* radii = a.radii ? a.radii : g.radii;
   g_prof.begin(6, s);
-  preprocess_bwd_kernel<<<(a.P + 127) / 128, 128, 0, s>>>(
-      a.P, a.D, a.M, a.means3D, radii, a.shs, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix,
-      a.projmatrix, focal_x, focal_y, a.tan_fovx, a.tan_fovy, a.cam_pos, g, a.dL_dmean2D, a.dL_dconic, a.dL_dopacity,
-      a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D, a.dL_dsh, a.dL_dscale, a.dL_drot, a.accumulate);
+  launch_pdl(preprocess_bwd_kernel, dim3((a.P + 127) / 128), dim3(128), 0, s, a.P, a.D, a.M, a.means3D, radii, a.shs,
+             a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp, a.viewmatrix, a.projmatrix, focal_x, focal_y,
+             a.tan_fovx, a.tan_fovy, a.cam_pos, g, a.dL_dmean2D, a.dL_dconic, a.dL_dopacity, a.dL_dcolor, a.dL_dmean3D,
+             a.dL_dcov3D, a.dL_dsh, a.dL_dscale, a.dL_drot, a.accumulate);
   g_prof.end(6, s);
   return cudaGetLastError();
 }

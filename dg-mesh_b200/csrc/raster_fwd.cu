@@ -141,6 +141,30 @@ __device__ __forceinline__ void for_each_tile_warp(const uint2 rmin, const uint2
   }
 }
 
+// depth -> bucket; monotone non-decreasing in the depth (same code in count and scatter).  The
+// range is either this frame's own (read from depth_range after preprocess) or a HINT passed by the
+// caller (the range of an earlier frame): any monotone map gives the same final order, the range
+// only decides how evenly the buckets fill, so a stale hint costs balance, never correctness.
+struct DepthBuckets {
+  float dmin, scale;
+  __device__ __forceinline__ DepthBuckets(float lo, float hi) { set(lo, hi); }
+  __device__ __forceinline__ DepthBuckets(const uint32_t* depth_range, int use_hint, float lo, float hi) {
+    if (use_hint) set(lo, hi);
+    else set(__uint_as_float(~depth_range[0]), __uint_as_float(depth_range[1]));
+  }
+  __device__ __forceinline__ void set(float lo, float hi) {
+    dmin = lo;
+    scale = (hi > lo) ? (float)DEPTH_BUCKETS / (hi - lo) : 0.0f;
+  }
+  __device__ __forceinline__ unsigned of(float depth) const {
+    const float x = (depth - dmin) * scale;
+    return min((unsigned)(DEPTH_BUCKETS - 1), (unsigned)max(x, 0.0f));
+  }
+};
+
+// COUNT: the (tile, depth bucket) histogram of count_kernel is built here as well (needs the
+// bucket range before the kernel starts, i.e. a hint)
+template <bool COUNT>
 __global__ void __launch_bounds__(256) preprocess_kernel(
     int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
     const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
@@ -148,9 +172,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
     int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int* __restrict__ radii_out,
     GeomWS g, unsigned gx, unsigned gy, uint32_t* __restrict__ depth_range, uint32_t* __restrict__ scan_flags,
-    int32_t* __restrict__ status, int prefiltered) {
+    int32_t* __restrict__ status, int prefiltered, uint32_t* __restrict__ hist, float hint_lo, float hint_hi) {
   __shared__ float s_cam[36];
   const unsigned tid = threadIdx.x;
+  pdl_wait();
+  pdl_launch();
   if (blockIdx.x == 0 && tid < 8) {  // state consumed by tile_scan_kernel, which runs after this grid
     scan_flags[tid] = 0;
     status[tid] = 0;
@@ -181,29 +207,24 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     atomicMax(&depth_range[0], dmin_inv);
     atomicMax(&depth_range[1], dmax);
   }
+  if (COUNT) {
+    const DepthBuckets db(hint_lo, hint_hi);
+    const unsigned long long bucket = ok ? db.of(g.depths[idx]) : 0u;
+    for_each_tile_warp(o.rmin, o.rmax, ok ? o.ntiles : 0u, gx, tid & 31, bucket, [&](unsigned t, unsigned long long b) {
+      atomicAdd(&hist[(size_t)t * DEPTH_BUCKETS + (unsigned)b], 1u);
+    });
+  }
 }
-
-// depth -> bucket; monotone non-decreasing in the depth (same code in count and scatter)
-struct DepthBuckets {
-  float dmin, scale;
-  __device__ __forceinline__ DepthBuckets(const uint32_t* depth_range) {
-    dmin = __uint_as_float(~depth_range[0]);
-    const float dmax = __uint_as_float(depth_range[1]);
-    scale = (dmax > dmin) ? (float)DEPTH_BUCKETS / (dmax - dmin) : 0.0f;
-  }
-  __device__ __forceinline__ unsigned of(float depth) const {
-    const float x = (depth - dmin) * scale;
-    return min((unsigned)(DEPTH_BUCKETS - 1), (unsigned)max(x, 0.0f));
-  }
-};
 
 // ================================================================ count ====
 __global__ void __launch_bounds__(256) count_kernel(int P, GeomWS g, uint32_t* __restrict__ hist,
                                                     const uint32_t* __restrict__ depth_range, unsigned gx,
                                                     unsigned gy) {
+  pdl_wait();
+  pdl_launch();
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
-  const DepthBuckets db(depth_range);
+  const DepthBuckets db(depth_range, 0, 0.f, 0.f);
   uint2 rmin = make_uint2(0, 0), rmax = make_uint2(0, 0);
   uint32_t ntiles = 0;
   unsigned long long bucket = 0;
@@ -231,12 +252,15 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(int T, uint32_t* __restr
                                                         uint32_t* __restrict__ tile_total, uint2* __restrict__ ranges,
                                                         uint32_t* __restrict__ tile_order,
                                                         uint32_t* __restrict__ flags, int32_t* __restrict__ status,
-                                                        long long R_cap) {
+                                                        long long R_cap, const uint32_t* __restrict__ depth_range,
+                                                        volatile int32_t* __restrict__ status_host) {
   __shared__ uint32_t s_part[8][33];
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_bucket[33];
   __shared__ uint32_t s_carry, s_last;
   const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_launch();
   {
     const int tx = tid & 31, seg = tid >> 5;
     const int t = blockIdx.x * 32 + tx;
@@ -326,8 +350,20 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(int T, uint32_t* __restr
     }
     status[0] = (int32_t)s_carry;
     status[1] = ((long long)s_carry > R_cap) ? 1 : 0;
+    // this frame's depth range (float bits; 0 / 0 when nothing is visible): the next call's hint
+    status[3] = depth_range[1] ? (int32_t)~depth_range[0] : 0;
+    status[4] = (int32_t)depth_range[1];
   }
   __syncthreads();
+  if (tid == 0 && status_host) {
+    // the caller's host-mapped copy (it waits for an event recorded behind this kernel)
+    status_host[0] = (int32_t)s_carry;
+    status_host[1] = ((long long)s_carry > R_cap) ? 1 : 0;
+    status_host[2] = *reinterpret_cast<volatile int32_t*>(status + 2);
+    status_host[3] = status[3];
+    status_host[4] = status[4];
+    __threadfence_system();
+  }
   for (int t = tid; t < T; t += 256) {
     const uint32_t c = __ldcg(tile_total + t);
     const uint32_t pos = atomicAdd(&s_bucket[c ? 32 - __clz(c) : 0], 1u);
@@ -344,11 +380,14 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, GeomWS g, const uin
                                                       uint32_t* __restrict__ hist,
                                                       const uint32_t* __restrict__ depth_range,
                                                       unsigned long long* __restrict__ keys, unsigned gx, unsigned gy,
-                                                      const int32_t* __restrict__ status) {
+                                                      const int32_t* __restrict__ status, int use_hint,
+                                                      float hint_lo, float hint_hi) {
+  pdl_wait();
+  pdl_launch();
   if (status[1]) return;  // overflow: nothing may be written
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
-  const DepthBuckets db(depth_range);
+  const DepthBuckets db(depth_range, use_hint, hint_lo, hint_hi);
   uint2 rmin = make_uint2(0, 0), rmax = make_uint2(0, 0);
   unsigned long long key = 0;
   uint32_t ntiles = 0;
@@ -414,6 +453,8 @@ __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __rest
                                                              const int32_t* __restrict__ status) {
   __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
   __shared__ uint32_t s_maxblock;
+  pdl_wait();
+  pdl_launch();
   if (status[1]) return;
   const uint2 range = ranges[blockIdx.x];
   const uint32_t n = range.y - range.x;
@@ -492,6 +533,8 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(const uint2* __restr
   __shared__ __align__(128) float4 s_attr[2][2 * RB];
   __shared__ __align__(8) uint64_t s_bar[2];
 
+  pdl_wait();
+  pdl_launch();
   const unsigned gx = (W + TILE_X - 1) / TILE_X;
   const unsigned tile = tile_order[blockIdx.x];  // longest lists first
   const unsigned tx = tile % gx, ty = tile / gx;
@@ -650,24 +693,37 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
   const int pblocks = (a.P + 255) / 256;
   // (tile, bucket) counters + the two depth-range words that follow them
   cudaMemsetAsync(im.hist, 0, sizeof(uint32_t) * ((size_t)T * DEPTH_BUCKETS + 8), s);
+  const int use_hint = (a.hint_hi > a.hint_lo) ? 1 : 0;
   g_prof.begin(0, s);
-  preprocess_kernel<<<pblocks, 256, 0, s>>>(
-      a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations, a.opacities, a.shs, a.cov3D_precomp,
-      a.colors_precomp, a.viewmatrix, a.projmatrix, a.cam_pos, a.W, a.H, a.tan_fovx, a.tan_fovy, focal_x, focal_y,
-      a.radii, g, gx, gy, im.depth_range, im.scan_flags, a.status, a.prefiltered);
-  g_prof.end(0, s);
-  g_prof.begin(7, s);
-  count_kernel<<<pblocks, 256, 0, s>>>(a.P, g, im.hist, im.depth_range, gx, gy);
-  g_prof.end(7, s);
+  if (use_hint) {
+    launch_pdl(preprocess_kernel<true>, dim3(pblocks), dim3(256), 0, s, a.P, a.D, a.M, a.means3D, a.scales,
+               a.scale_modifier, a.rotations, a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp, a.viewmatrix,
+               a.projmatrix, a.cam_pos, a.W, a.H, a.tan_fovx, a.tan_fovy, focal_x, focal_y, a.radii, g, gx, gy,
+               im.depth_range, im.scan_flags, a.status, a.prefiltered, im.hist, a.hint_lo, a.hint_hi);
+    g_prof.end(0, s);
+  } else {
+    launch_pdl(preprocess_kernel<false>, dim3(pblocks), dim3(256), 0, s, a.P, a.D, a.M, a.means3D, a.scales,
+               a.scale_modifier, a.rotations, a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp, a.viewmatrix,
+               a.projmatrix, a.cam_pos, a.W, a.H, a.tan_fovx, a.tan_fovy, focal_x, focal_y, a.radii, g, gx, gy,
+               im.depth_range, im.scan_flags, a.status, a.prefiltered, im.hist, 0.f, 0.f);
+    g_prof.end(0, s);
+    g_prof.begin(7, s);
+    launch_pdl(count_kernel, dim3(pblocks), dim3(256), 0, s, a.P, g, im.hist, (const uint32_t*)im.depth_range, gx, gy);
+    g_prof.end(7, s);
+  }
   g_prof.begin(1, s);
-  tile_scan_kernel<<<(T + 31) / 32, 256, 0, s>>>(T, im.hist, im.tile_total, im.ranges, im.tile_order, im.scan_flags,
-                                                 a.status, (long long)a.R_cap);
+  launch_pdl(tile_scan_kernel, dim3((T + 31) / 32), dim3(256), 0, s, T, im.hist, im.tile_total, im.ranges,
+             im.tile_order, im.scan_flags, a.status, (long long)a.R_cap, (const uint32_t*)im.depth_range,
+             (volatile int32_t*)a.status_host);
   g_prof.end(1, s);
+  if (a.status_event) cudaEventRecord(a.status_event, s);
   g_prof.begin(2, s);
-  scatter_kernel<<<pblocks, 256, 0, s>>>(a.P, g, im.ranges, im.hist, im.depth_range, b.keys, gx, gy, a.status);
+  launch_pdl(scatter_kernel, dim3(pblocks), dim3(256), 0, s, a.P, g, (const uint2*)im.ranges, im.hist,
+             (const uint32_t*)im.depth_range, b.keys, gx, gy, (const int32_t*)a.status, use_hint, a.hint_lo, a.hint_hi);
   g_prof.end(2, s);
   g_prof.begin(3, s);
-  tile_sort_pack_kernel<<<T, 256, 0, s>>>(im.ranges, b.keys, im.hist, g, a.colors_precomp, b, a.status);
+  launch_pdl(tile_sort_pack_kernel, dim3(T), dim3(256), 0, s, (const uint2*)im.ranges, b.keys,
+             (const uint32_t*)im.hist, g, a.colors_precomp, b, (const int32_t*)a.status);
   g_prof.end(3, s);
   return cudaGetLastError();
 }
@@ -679,8 +735,9 @@ cudaError_t launch_render(const FwdArgs& a, cudaStream_t s) {
   ImgWS im = ImgWS::from((char*)a.img_ws, (size_t)a.W * a.H, T);
   BinWS b = BinWS::from((char*)a.binning_ws, (size_t)a.R_cap);
   g_prof.begin(4, s);
-  render_fwd_kernel<<<T, 256, 0, s>>>(im.ranges, im.tile_order, b.inst_geo, b.inst_attr, a.W, a.H, a.background,
-                                      im.final_T, im.n_contrib, a.out_color, a.status);
+  launch_pdl(render_fwd_kernel, dim3(T), dim3(256), 0, s, (const uint2*)im.ranges, (const uint32_t*)im.tile_order,
+             (const float4*)b.inst_geo, (const float4*)b.inst_attr, a.W, a.H, a.background, im.final_T, im.n_contrib,
+             a.out_color, (const int32_t*)a.status);
   g_prof.end(4, s);
   return cudaGetLastError();
 }

@@ -20,6 +20,11 @@ struct FwdArgs {
   void *geom_ws, *binning_ws, *img_ws;
   int64_t R_cap;
   int32_t* status;
+  // optional: host-mapped (pinned) copy of the status words, written by the tile scan, and the
+  // depth range of an earlier frame (hint_hi > hint_lo enables the fused preprocess + count)
+  int32_t* status_host;
+  float hint_lo, hint_hi;
+  cudaEvent_t status_event;  // recorded right after the tile scan (may be null)
 };
 
 struct BwdArgs {
@@ -35,7 +40,8 @@ struct BwdArgs {
   int64_t R_cap;
   const float* dL_dpix;
   float *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor, *dL_dmean3D, *dL_dcov3D, *dL_dsh, *dL_dscale, *dL_drot;
-  int accumulate;  // 0: parameter gradients are written; 1: added to what the buffers hold (frame batches)
+  int accumulate;  // bit mask DGR_PF_*: outputs that are ADDED to what the buffers hold (shared inputs of a
+                   // frame batch, frames after the first); 0: every parameter gradient is written
 };
 
 // event pairs around kernels (see dgm_profile_enable in include/dgmesh_b200.h)

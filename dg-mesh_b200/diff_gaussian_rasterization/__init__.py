@@ -9,15 +9,16 @@ Mirrors the reference Python surface
                                  (dgr/ext.cpp:15-19, dgr/rasterize_points.h:18-66)
 
 Differences that are deliberate:
-  * the autograd path never copies num_rendered to the host; R stays in a device
-    status block.  The instance workspace is sized from a high-water mark; an overflow
-    is detected when the status block is next read and raises (no silent truncation).
-    Set DGMESH_B200_SYNC=1 to size exactly with one host sync per forward, like the
-    reference (rasterizer_impl.cu:281).
+  * where the reference blocks on a copy of num_rendered in the middle of the forward
+    (rasterizer_impl.cu:281), this enqueues the whole forward optimistically and waits only for
+    an event recorded behind the tile scan (the rest stays queued); a frame that did not fit the
+    instance workspace is re-run with the right capacity before the image is returned
+    (`_Sizing`): every result is exact, nothing is raised later.
   * work is enqueued on the CURRENT torch stream (the reference uses the legacy
     default stream).
 """
 import os
+import struct
 import sys
 from typing import NamedTuple
 
@@ -30,7 +31,7 @@ if _root not in sys.path:
 import _dgm_lib  # noqa: E402
 
 _ST_WORDS = 8
-_SYNC = os.environ.get("DGMESH_B200_SYNC", "0") == "1"
+_MAX_FRAMES = 63
 
 
 def _f32c(t, name):
@@ -43,57 +44,91 @@ def _f32c(t, name):
     return t.contiguous()
 
 
+class _Notify:
+    """Per-device early-notification object (dgm_notify_*): an event recorded right behind the tile
+    scan and a device-mapped pinned mirror of the status words, read here through ctypes."""
+    _per_device = {}
+
+    def __init__(self):
+        h = _dgm_lib.c_void_p()
+        _dgm_lib.check(_dgm_lib.lib().dgm_notify_create(_dgm_lib.byref(h)), "dgm_notify_create")
+        self.handle = h
+        self.event = _dgm_lib.lib().dgm_notify_event(h)
+        self.host_ptr = _dgm_lib.lib().dgm_notify_host(h)
+        self.words = (_dgm_lib.c_int32 * (64 * _ST_WORDS)).from_address(self.host_ptr)
+
+    @classmethod
+    def get(cls, dev_index):
+        n = cls._per_device.get(dev_index)
+        if n is None:
+            n = cls._per_device[dev_index] = _Notify()
+        return n
+
+    def wait(self):
+        _dgm_lib.check(_dgm_lib.lib().dgm_notify_wait(self.handle), "dgm_notify_wait")
+
+
+def _bits_to_float(v):
+    return struct.unpack("f", struct.pack("i", int(v)))[0]
+
+
 class _Sizing:
-    """High-water-mark capacity of the (Gaussian, tile) instance workspace per problem shape."""
-    hint = {}       # (device, P, W, H) -> R capacity
-    pending = []    # [(event, pinned status, key, R_cap)] forwards whose status was not read yet
-    free = []       # recycled (event, pinned buffer) pairs
+    """Capacity of the (Gaussian, tile) instance workspace and the depth-range hint, per image shape.
+
+    The reference learns R with a blocking copy in the middle of every forward
+    (rasterizer_impl.cu:281) and sizes its binning buffers exactly.  Here a forward is enqueued
+    optimistically with the capacity the last frames needed (plus head-room); the tile scan
+    mirrors the status words into pinned host memory and an event is recorded behind it, and the
+    host waits for THAT event before returning -- the remaining 4/5 of the forward are still queued,
+    so the GPU never idles.  If the frame did not fit (first frame of a shape, a close-up, after
+    densification), the enqueued kernels skip themselves and the forward is re-run with the right
+    capacity before the caller ever sees the image: results are exact in every case, no exception,
+    no background-only frame."""
+    hint = {}       # (device, W, H) -> [R capacity, depth lo, depth hi]
 
     @classmethod
-    def watch(cls, status, key, cap):
-        """Queue an asynchronous read-back of a forward's status block (no host sync)."""
-        if torch.cuda.is_current_stream_capturing():
-            return  # CUDA-graph capture: no host-side polling; the capacity comes from the eager warm-up
-        if cls.free:
-            ev, host = cls.free.pop()
-        else:
-            ev, host = torch.cuda.Event(), torch.empty((64 * _ST_WORDS,), dtype=torch.int32, pin_memory=True)
-        n = status.numel()
-        host[:n].copy_(status.reshape(-1), non_blocking=True)
-        host[n:n + 1].fill_(-1) if n < host.numel() else None
-        ev.record()
-        cls.pending.append((ev, host, key, cap))
+    def lookup(cls, key, P):
+        h = cls.hint.get(key)
+        if h is None:
+            return _round_cap(max(4 * P, 1 << 18)), 0.0, 0.0
+        return h[0], h[1], h[2]
 
     @classmethod
-    def poll(cls, block=False):
-        if not cls.pending or torch.cuda.is_current_stream_capturing():
-            return
-        still = []
-        err = None
-        for item in cls.pending:
-            ev, host, key, cap = item
-            if block:
-                ev.synchronize()
-            if block or ev.query():
-                R, ovf = 0, 0
-                for f in range(64):  # one 8-word block per frame, terminated by -1
-                    if int(host[8 * f]) < 0:
-                        break
-                    R, ovf = max(R, int(host[8 * f])), ovf | int(host[8 * f + 1])
-                g = _grow(R)
-                if g > cls.hint.get(key, 0):
-                    cls.hint[key] = g
-                if ovf:
-                    err = (R, cap)
-                cls.free.append((ev, host))
-            else:
-                still.append(item)
-        cls.pending = still
-        if err is not None:
-            raise _dgm_lib.DgmError(
-                f"rasterizer instance workspace overflowed in an earlier forward (R={err[0]} > capacity {err[1]}); "
-                "that render was background-only. Capacity has been raised; re-run the step "
-                "(or set DGMESH_B200_SYNC=1 for exact sizing with a host sync).")
+    def update(cls, key, R, lo, hi):
+        h = cls.hint.get(key)
+        if h is None:
+            if len(cls.hint) >= 64:      # bounded: image shapes seen by one process
+                cls.hint.clear()
+            h = cls.hint[key] = [0, 0.0, 0.0]
+        h[0] = max(h[0], _grow(R))
+        if hi > lo:
+            h[1], h[2] = lo, hi
+
+
+def _run_sized(enqueue, key, P, dev_index, F=1):
+    """enqueue(R_cap, notify, lo, hi) -> outputs.  Returns (outputs, R of the largest frame)."""
+    cap, lo, hi = _Sizing.lookup(key, P)
+    if torch.cuda.is_current_stream_capturing():
+        # CUDA-graph capture: no host-side waiting; the capacity comes from the eager warm-up and an
+        # overflow (status word 1) would replay as a background frame -- callers of graph replay check
+        # `last_status()`; bench.py does
+        return enqueue(cap, None, lo, hi), None
+    nt = _Notify.get(dev_index)
+    out = enqueue(cap, nt, lo, hi)
+    nt.wait()
+    w = nt.words
+    R = max(w[_ST_WORDS * f] for f in range(F))
+    ovf = any(w[_ST_WORDS * f + 1] for f in range(F))
+    dlo = min((_bits_to_float(w[_ST_WORDS * f + 3]) for f in range(F) if w[_ST_WORDS * f + 4]), default=0.0)
+    dhi = max((_bits_to_float(w[_ST_WORDS * f + 4]) for f in range(F) if w[_ST_WORDS * f + 4]), default=0.0)
+    _Sizing.update(key, R, dlo, dhi)
+    if ovf:
+        cap, lo, hi = _Sizing.lookup(key, P)
+        out = enqueue(cap, nt, lo, hi)   # same inputs, capacity >= R: cannot overflow again
+        nt.wait()
+        if any(w[_ST_WORDS * f + 1] for f in range(F)):
+            raise _dgm_lib.DgmError("rasterizer: instance workspace overflow persisted after regrowth")
+    return out, R
 
 
 def _round_cap(c):
@@ -150,7 +185,8 @@ class _Workspace:
 
 
 def _raw_forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
-                 projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered, R_cap):
+                 projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered, R_cap, notify=None,
+                 lo=0.0, hi=0.0, out=None):
     """One enqueue of dgr_forward.  Returns (color, radii, workspace)."""
     lib = _dgm_lib.lib()
     if means3D.ndim != 2 or means3D.shape[1] != 3:
@@ -159,36 +195,20 @@ def _raw_forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier
     P = means3D.shape[0]
     M = int(sh.shape[1]) if (sh is not None and sh.numel() != 0) else 0
     ws = _Workspace(P, W, H, R_cap, dev)
-    color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    if out is None:
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    else:
+        color, radii = out      # a re-run after an overflow writes the tensors of the first attempt
     p = _dgm_lib.ptr
     rc = lib.dgr_forward(P, degree, M, p(bg), W, H, p(means3D), p(sh), p(colors), p(opacity), p(scales),
                          float(scale_modifier), p(rotations), p(cov3D_precomp), p(viewmatrix), p(projmatrix),
                          p(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), p(color), p(radii),
                          ws.geom, ws.gb, ws.binning, ws.bb, R_cap, ws.img, ws.ib, ws.status,
+                         notify.host_ptr if notify else None, notify.event if notify else None, lo, hi,
                          _dgm_lib.stream_ptr())
     _dgm_lib.check(rc, "dgr_forward")
     return color, radii, ws
-
-
-def _forward_sized(args_fn, key, sync):
-    """Run the forward with a capacity policy.  args_fn(R_cap) enqueues and returns (color, radii, ws)."""
-    _Sizing.poll()
-    cap = _Sizing.hint.get(key)
-    if cap is None or sync:
-        # first call for this shape (or strict mode): size exactly, one host sync
-        cap0 = cap if cap is not None else _round_cap(max(4 * key[1], 1 << 18))
-        out = args_fn(cap0)
-        st = out[2].status_tensor().cpu()
-        R = int(st[0])
-        _Sizing.hint[key] = max(_Sizing.hint.get(key, 0), _grow(R))
-        if int(st[1]):
-            cap0 = _Sizing.hint[key]
-            out = args_fn(cap0)
-        return out, R
-    out = args_fn(cap)
-    _Sizing.watch(out[2].status_tensor(), key, cap)
-    return out, None
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
@@ -211,14 +231,21 @@ class _RasterizeGaussians(torch.autograd.Function):
              _f32c(rs.projmatrix, "projmatrix"), _f32c(rs.campos, "campos"))
         bg, sh_, col, opac, sc, rot, cov, view, proj, campos = t
         H, W = int(rs.image_height), int(rs.image_width)
-        key = (means3D.device.index, means3D.shape[0], W, H)
+        dev_index = means3D.device.index
+        key = (dev_index, W, H)
+        first = []
 
-        def run(R_cap):
-            return _raw_forward(bg, means3D, col, opac, sc, rot, rs.scale_modifier, cov, view, proj, rs.tanfovx,
-                                rs.tanfovy, H, W, sh_, rs.sh_degree, campos, rs.prefiltered, R_cap)
+        def run(R_cap, notify, lo, hi):
+            o = _raw_forward(bg, means3D, col, opac, sc, rot, rs.scale_modifier, cov, view, proj, rs.tanfovx,
+                             rs.tanfovy, H, W, sh_, rs.sh_degree, campos, rs.prefiltered, R_cap, notify, lo, hi,
+                             first[0] if first else None)
+            if not first:
+                first.append(o[:2])
+            return o
 
-        sync = bool(rs.debug) or _SYNC
-        (color, radii, ws), _ = _forward_sized(run, key, sync)
+        (color, radii, ws), _ = _run_sized(run, key, means3D.shape[0], dev_index)
+        if rs.debug:
+            torch.cuda.current_stream().synchronize()   # the reference's debug mode checks after every kernel
         ctx.raster_settings = rs
         ctx.ws = ws
         ctx.R_cap = ws.R_cap
@@ -234,9 +261,6 @@ class _RasterizeGaussians(torch.autograd.Function):
         bg, sh, col, opac, sc, rot, cov, view, proj, campos = ctx.tensors
         means3D, radii = ctx.saved_tensors
         ws = ctx.ws
-        # No host wait here: if the forward overflowed, its image is background-only with n_contrib = 0,
-        # so this backward produces exact zeros; the overflow itself is raised at the next poll.
-        _Sizing.poll()
         lib = _dgm_lib.lib()
         P = means3D.shape[0]
         H, W = int(rs.image_height), int(rs.image_width)
@@ -281,8 +305,6 @@ class _BatchWorkspace:
 
     def __init__(self, F, P, W, H, R_cap, dev):
         _, _, _, ga, ba, ia = _sizes(P, W, H, R_cap)
-        if F > 63:
-            raise ValueError("at most 63 frames per batch")
         self.buf = torch.empty((F * (ga + ba + ia) + 32 * F,), dtype=torch.uint8, device=dev)
         base = self.buf.data_ptr()
         self.geom, self.binning, self.img = base, base + F * ga, base + F * (ga + ba)
@@ -311,15 +333,24 @@ def _stack_settings(settings, dev):
     return views, projs, cams, tx, ty
 
 
+_PF_MEANS, _PF_SCALES, _PF_ROTS, _PF_OPAC, _PF_COLOR, _PF_COV = 1, 2, 4, 8, 16, 32
+
+
 class _RasterizeGaussiansBatch(torch.autograd.Function):
-    """F frames over one set of Gaussians: colors [F,3,H,W], radii [F,P].  Gradients of the
-    Gaussian parameters are the SUM over frames (accumulated inside the kernels); means2D, if given
-    as an [F,P,3] tensor, receives the per-frame screen-space gradients."""
+    """F frames in one call: colors [F,3,H,W], radii [F,P].
+
+    Every Gaussian input may be SHARED ([P,.] -- its gradient is the sum over frames, accumulated
+    inside the kernels) or PER FRAME (a leading F dimension, [F,P,.] -- its gradient is [F,P,.]).
+    DG-Mesh's dynamic scenes deform means / scales / rotations by the frame's time
+    (gaussian_renderer/__init__.py:60-86), so those arrive per frame while opacity and SH are shared.
+    means2D, if given as an [F,P,3] tensor, receives the per-frame screen-space gradients."""
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings):
         rs0 = settings[0]
         F = len(settings)
+        if F > _MAX_FRAMES:
+            raise ValueError(f"at most {_MAX_FRAMES} frames per batch")
         for s in settings:
             if (s.image_height, s.image_width, s.sh_degree, s.scale_modifier) != \
                     (rs0.image_height, rs0.image_width, rs0.sh_degree, rs0.scale_modifier):
@@ -331,40 +362,48 @@ class _RasterizeGaussiansBatch(torch.autograd.Function):
              _f32c(opacities, "opacities"), _f32c(scales, "scales"), _f32c(rotations, "rotations"),
              _f32c(cov3Ds_precomp, "cov3D_precomp"))
         bg, sh_, col, opac, sc, rot, cov = t
+        # per-frame mask from the ranks: means [F,P,3], scales [F,P,3], rotations [F,P,4], opacities [F,P,1],
+        # shs [F,P,M,3] / colors [F,P,3], cov3D [F,P,6]
+        pf = 0
+        for x, rank, bit in ((means3D, 3, _PF_MEANS), (sc, 3, _PF_SCALES), (rot, 3, _PF_ROTS), (opac, 3, _PF_OPAC),
+                             (sh_, 4, _PF_COLOR), (col, 3, _PF_COLOR), (cov, 3, _PF_COV)):
+            if x is not None and x.ndim == rank:
+                if x.shape[0] != F:
+                    raise ValueError("per-frame inputs must have a leading dimension equal to the number of frames")
+                pf |= bit
+        P = means3D.shape[-2]
+        if means3D.shape[-1] != 3:
+            raise ValueError("means3D must have dimensions (num_points, 3)")
         dev = means3D.device
         views, projs, cams, tx, ty = _stack_settings(settings, dev)
-        P, H, W = means3D.shape[0], int(rs0.image_height), int(rs0.image_width)
-        M = int(sh_.shape[1]) if sh_ is not None else 0
-        key = (dev.index, P, W, H)
+        H, W = int(rs0.image_height), int(rs0.image_width)
+        M = int(sh_.shape[-2]) if sh_ is not None else 0
+        key = (dev.index, W, H)
         lib = _dgm_lib.lib()
         p = _dgm_lib.ptr
+        first = []
 
-        def run(R_cap):
+        def run(R_cap, notify, lo, hi):
             ws = _BatchWorkspace(F, P, W, H, R_cap, dev)
-            color = torch.empty((F, 3, H, W), dtype=torch.float32, device=dev)
-            radii = torch.empty((F, P), dtype=torch.int32, device=dev)
+            if first:
+                color, radii = first[0]
+            else:
+                color = torch.empty((F, 3, H, W), dtype=torch.float32, device=dev)
+                radii = torch.empty((F, P), dtype=torch.int32, device=dev)
+                first.append((color, radii))
             rc = lib.dgr_forward_batch(F, P, rs0.sh_degree, M, p(bg), W, H, p(means3D), p(sh_), p(col), p(opac),
-                                       p(sc), float(rs0.scale_modifier), p(rot), p(cov), p(views), p(projs), p(cams),
-                                       tx, ty, int(bool(rs0.prefiltered)), p(color), p(radii), ws.geom, ws.gs,
-                                       ws.binning, ws.bs, R_cap, ws.img, ws.is_, ws.status, _N_STREAMS,
-                                       _dgm_lib.stream_ptr())
+                                       p(sc), float(rs0.scale_modifier), p(rot), p(cov), pf, p(views), p(projs),
+                                       p(cams), tx, ty, int(bool(rs0.prefiltered)), p(color), p(radii), ws.geom, ws.gs,
+                                       ws.binning, ws.bs, R_cap, ws.img, ws.is_, ws.status,
+                                       notify.host_ptr if notify else None, notify.event if notify else None, lo, hi,
+                                       _N_STREAMS, _dgm_lib.stream_ptr())
             _dgm_lib.check(rc, "dgr_forward_batch")
             return color, radii, ws
 
-        _Sizing.poll()
-        cap = _Sizing.hint.get(key)
-        if cap is None or _SYNC or rs0.debug:
-            cap0 = cap if cap is not None else _round_cap(max(4 * P, 1 << 18))
-            color, radii, ws = run(cap0)
-            st = ws.status_tensor().cpu()
-            _Sizing.hint[key] = max(_Sizing.hint.get(key, 0), _grow(int(st[:, 0].max())))
-            if int(st[:, 1].max()):
-                color, radii, ws = run(_Sizing.hint[key])
-        else:
-            color, radii, ws = run(cap)
-            _Sizing.watch(ws.status_tensor(), key, cap)
+        (color, radii, ws), _ = _run_sized(run, key, P, dev.index, F)
         ctx.ws, ctx.tensors, ctx.cams, ctx.settings = ws, t, (views, projs, cams, tx, ty), settings
         ctx.has_m2d = means2D is not None
+        ctx.pf = pf
         ctx.save_for_backward(means3D, radii)
         ctx.mark_non_differentiable(radii)
         return color, radii
@@ -374,37 +413,47 @@ class _RasterizeGaussiansBatch(torch.autograd.Function):
         bg, sh, col, opac, sc, rot, cov = ctx.tensors
         views, projs, cams, tx, ty = ctx.cams
         means3D, radii = ctx.saved_tensors
-        ws, rs0 = ctx.ws, ctx.settings[0]
-        _Sizing.poll()  # non-blocking (an overflowed forward back-propagates zeros, see _RasterizeGaussians)
-        F, P = ws.F, means3D.shape[0]
+        ws, rs0, pf = ctx.ws, ctx.settings[0], ctx.pf
+        F, P = ws.F, means3D.shape[-2]
         H, W = int(rs0.image_height), int(rs0.image_width)
-        M = int(sh.shape[1]) if sh is not None else 0
+        M = int(sh.shape[-2]) if sh is not None else 0
+
+        def nf(bit):
+            return F if (pf & bit) else 1
+
+        # m2d[F,P,3] opac col m3d cov scale rot sh -- per-frame inputs get F slabs
+        widths = (3 * F, nf(_PF_OPAC), 3 * (nf(_PF_COLOR) if sh is None else 1), 3 * nf(_PF_MEANS),
+                  6 * nf(_PF_COV), 3 * nf(_PF_SCALES), 4 * nf(_PF_ROTS), 3 * M * nf(_PF_COLOR))
         offs, o = [], 0
-        for w in (3 * F, 1, 3, 3, 6, 3, 4, 3 * M):  # m2d[F,P,3] opac col m3d cov scale rot sh
+        for w in widths:
             offs.append(o)
             o = (o + P * w + 3) // 4 * 4
         flat = torch.empty((max(o, 1),), dtype=torch.float32, device=means3D.device)
         base = flat.data_ptr()
         ptrs = [base + 4 * x for x in offs]
 
-        def gview(i, *shape):
+        def gview(i, bit, *shape):
             n = 1
             for d in shape:
                 n *= d
+            if bit and (pf & bit):
+                return flat[offs[i]:offs[i] + F * n].view(F, *shape)
             return flat[offs[i]:offs[i] + n].view(*shape)
 
         dpix = _f32c(grad_out_color, "grad_out_color")
         p = _dgm_lib.ptr
         rc = _dgm_lib.lib().dgr_backward_batch(
             F, P, rs0.sh_degree, M, p(bg), W, H, p(means3D), p(sh), p(col), p(sc), float(rs0.scale_modifier), p(rot),
-            p(cov), p(views), p(projs), p(cams), tx, ty, p(radii), ws.geom, ws.gs, ws.binning, ws.bs, ws.R_cap,
+            p(cov), pf, p(views), p(projs), p(cams), tx, ty, p(radii), ws.geom, ws.gs, ws.binning, ws.bs, ws.R_cap,
             ws.img, ws.is_, p(dpix), ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[7] if M else None, ptrs[5],
             ptrs[6], _N_STREAMS, _dgm_lib.stream_ptr())
         _dgm_lib.check(rc, "dgr_backward_batch")
-        return (gview(3, P, 3), gview(0, F, P, 3) if ctx.has_m2d else None,
-                gview(7, P, M, 3) if sh is not None else None, gview(2, P, 3) if col is not None else None,
-                gview(1, P, 1), gview(5, P, 3) if sc is not None else None,
-                gview(6, P, 4) if rot is not None else None, gview(4, P, 6) if cov is not None else None, None)
+        return (gview(3, _PF_MEANS, P, 3), gview(0, 0, F, P, 3) if ctx.has_m2d else None,
+                gview(7, _PF_COLOR, P, M, 3) if sh is not None else None,
+                gview(2, _PF_COLOR, P, 3) if col is not None else None,
+                gview(1, _PF_OPAC, P, 1), gview(5, _PF_SCALES, P, 3) if sc is not None else None,
+                gview(6, _PF_ROTS, P, 4) if rot is not None else None,
+                gview(4, _PF_COV, P, 6) if cov is not None else None, None)
 
 
 def rasterize_gaussians_batch(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
@@ -498,13 +547,20 @@ class _CCompat:
         bg_, m3, col, op, sc, ro, cov, view, proj, sh_, cam = a
         if m3 is None:
             raise ValueError("means3D must have dimensions (num_points, 3)")
-        key = (m3.device.index, m3.shape[0], int(image_width), int(image_height))
+        key = (m3.device.index, int(image_width), int(image_height))
+        first = []
 
-        def run(R_cap):
-            return _raw_forward(bg_, m3, col, op, sc, ro, scale_modifier, cov, view, proj, tan_fovx, tan_fovy,
-                                int(image_height), int(image_width), sh_, degree, cam, prefiltered, R_cap)
+        def run(R_cap, notify, lo, hi):
+            o = _raw_forward(bg_, m3, col, op, sc, ro, scale_modifier, cov, view, proj, tan_fovx, tan_fovy,
+                             int(image_height), int(image_width), sh_, degree, cam, prefiltered, R_cap, notify, lo, hi,
+                             first[0] if first else None)
+            if not first:
+                first.append(o[:2])
+            return o
 
-        (color, radii, ws), R = _forward_sized(run, key, True)
+        (color, radii, ws), R = _run_sized(run, key, m3.shape[0], m3.device.index)
+        if R is None:       # stream capture: this entry point returns R as a Python int and cannot be captured
+            raise _dgm_lib.DgmError("_C.rasterize_gaussians returns num_rendered to the host: not capturable")
         # the three opaque byte tensors (views of one allocation) carry everything backward needs;
         # the capacity is implied by the size of the binning buffer
         geom, binning, img = ws.split()

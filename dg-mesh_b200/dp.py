@@ -17,25 +17,63 @@ def shard_frames(n_frames, rank, world):
 
 
 class FlatGrad:
-    """Gradients of `params` as views of ONE flat buffer, so the exchange is a single collective."""
+    """Gradients of `params` as views of ONE flat buffer, so the exchange is a single collective.
+
+    The views are installed as `p.grad`.  A training loop may break that aliasing -- the reference's
+    `optimizer.zero_grad(set_to_none=True)` (dgmesh/train.py:525-530) drops the views, and
+    densification replaces the Parameter objects altogether -- so `allreduce()` verifies every binding
+    first: a detached `p.grad` is copied into its slice and re-bound (correct result, one extra copy), a
+    missing one counts as zero, and a parameter list whose shapes changed raises.  After densify / prune
+    call `rebuild(new_params)`; use `zero()` (or `zero_grad(set_to_none=False)`) to keep the fast path."""
 
     def __init__(self, params):
+        self.rebuild(params)
+
+    def rebuild(self, params):
+        """(Re)create the flat buffer for a new parameter list (after densification / pruning)."""
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FlatGrad: no parameter requires grad")
         dev, dt = self.params[0].device, torch.float32
         self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=dt)
-        off = 0
+        self.offsets, self.shapes, off = [], [], 0
         for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+            self.offsets.append(off)
+            self.shapes.append(tuple(p.shape))
+            off += p.numel()
+        self._bind(copy=False)
+
+    def _slice(self, i):
+        if tuple(self.params[i].shape) != self.shapes[i]:
+            raise RuntimeError("FlatGrad: a parameter changed shape; call rebuild(params) after densify / prune")
+        n = 1
+        for d in self.shapes[i]:
+            n *= d
+        return self.flat[self.offsets[i]:self.offsets[i] + n].view(self.shapes[i])
+
+    def _bind(self, copy):
+        """Make every p.grad a view of the flat buffer; returns how many had to be re-bound."""
+        rebound = 0
+        for i, p in enumerate(self.params):
+            v = self._slice(i)
+            g = p.grad
+            if g is not None and g.data_ptr() == v.data_ptr() and g.shape == v.shape:
+                continue
+            if copy:
+                if g is None:
+                    v.zero_()          # no gradient this step (e.g. zero_grad(set_to_none=True) and unused)
+                else:
+                    v.copy_(g)
+            p.grad = v
+            rebound += 1
+        return rebound
 
     def zero(self):
         self.flat.zero_()
 
     def allreduce(self, average=True, group=None):
         """Sum (or mean) of the gradients over the ranks; no-op for a single process."""
+        self._bind(copy=True)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             if average:

@@ -6,10 +6,16 @@ forward + backward run as bf16 tcgen05 GEMM chains inside libdgmesh_b200.so.
 `utils` is a namespace package in the reference (no __init__.py) and here: with this directory
 ahead of the reference's on sys.path only `utils.time_utils` is replaced.
 
-Numerics: bf16 operands, fp32 accumulation (the reference is fp32 cuBLAS).  Against a bf16-rounding
-restatement the outputs agree to ~1e-3 of their scale; the gap to the fp32 reference (~1e-2 relative
-on the deltas) is reported by tests/test_mlp.py and DESIGN.md.  is_6dof (off in every reference
-config) is not implemented and raises.
+Numerics (the reference is fp32 cuBLAS).  Default `DGMESH_B200_MLP_PRECISION=bf16x3`: the forward
+runs every layer as three bf16 tcgen05 passes over split operands (hi + lo, fp32 accumulation), so
+outputs agree with the fp32 reference to ~1e-5 and the ReLU decisions are the reference's; the
+backward is single-pass bf16 and the parameter / input gradients agree to <= 2 % relative L2
+(measured 0.3-1 %).  `bf16`: single-pass forward, 3x fewer MMAs; outputs ~2e-3, but ~1 % of the
+ReLU signs flip and gradients differ by ~7 % (tests/test_mlp.py).  is_6dof (off in every
+reference config) is not implemented and raises.
+
+The packed bf16 operands are cached per module and rebuilt only when a parameter changed (tensor
+version counters), i.e. once per optimiser step, not once per forward.
 """
 import ctypes
 import os
@@ -24,6 +30,15 @@ if _root not in sys.path:
 import _dgm_lib  # noqa: E402
 
 _sizes = None
+_PRECISE = os.environ.get("DGMESH_B200_MLP_PRECISION", "bf16x3").lower() != "bf16"
+
+
+def set_precision(mode):
+    """'bf16x3' (default: split-precision forward) or 'bf16' (single pass)."""
+    global _PRECISE
+    if mode not in ("bf16x3", "bf16"):
+        raise ValueError("precision must be 'bf16x3' or 'bf16'")
+    _PRECISE = mode == "bf16x3"
 
 
 def _pack_sizes():
@@ -67,15 +82,23 @@ class _MLPFunction(torch.autograd.Function):
         if xc.dim() != 2 or xc.shape[1] != 3 or tc.shape[0] != P:
             raise ValueError("expected x [N,3] and t [N,1]")
         dev = xc.device
-        ps = [p.detach().contiguous().float() for p in params]
-        wb, bb, _ = _pack_sizes()
-        wbuf = torch.empty((wb,), dtype=torch.uint8, device=dev)
-        bbuf = torch.empty((bb // 4,), dtype=torch.float32, device=dev)
-        raw = _raw_struct(_dgm_lib.DglRaw, spec, ps)
-        net = _dgm_lib.DglNet()
         st = _dgm_lib.stream_ptr()
-        _dgm_lib.check(lib.dgl_mlp_pack(ctypes.byref(raw), wbuf.data_ptr(), bbuf.data_ptr(), ctypes.byref(net), st),
-                       "dgl_mlp_pack")
+        # packed operands: rebuilt only when some parameter was modified since they were packed
+        sig = tuple((p.data_ptr(), p._version) for p in params) + (st,)
+        cache = spec.get("_packed")
+        if cache is not None and cache[0] == sig and not torch.cuda.is_current_stream_capturing():
+            _, wbuf, bbuf, ps, raw, net = cache
+        else:
+            ps = [p.detach().contiguous().float() for p in params]
+            wb, bb, _ = _pack_sizes()
+            wbuf = torch.empty((wb,), dtype=torch.uint8, device=dev)
+            bbuf = torch.empty((bb // 4,), dtype=torch.float32, device=dev)
+            raw = _raw_struct(_dgm_lib.DglRaw, spec, ps)
+            net = _dgm_lib.DglNet()
+            _dgm_lib.check(lib.dgl_mlp_pack(ctypes.byref(raw), wbuf.data_ptr(), bbuf.data_ptr(), ctypes.byref(net),
+                                            st), "dgl_mlp_pack")
+            spec["_packed"] = (sig, wbuf, bbuf, ps, raw, net)
+        net.precise = int(_PRECISE)
         train = int(train)   # decided by the caller: grad mode is always off inside Function.forward
         nbytes = _dgm_lib.c_size_t()
         _dgm_lib.check(lib.dgl_mlp_workspace(P, train, ctypes.byref(nbytes)), "dgl_mlp_workspace")

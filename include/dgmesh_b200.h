@@ -38,6 +38,17 @@ const char* dgm_version(void);
 /* cudaGetErrorString of the last launch error seen by this thread (or "") */
 const char* dgm_last_error(void);
 
+/* Early-notification object for dgr_forward / dgr_forward_batch (see there): a CUDA event
+ * plus a pinned, device-mapped host array of 64 status blocks (int32[64 * DGR_STATUS_WORDS]).
+ * Stands in for the reference's blocking cudaMemcpy of num_rendered
+ * (rasterizer_impl.cu:281): the caller waits for the event instead, with the rest of the
+ * forward already queued.  dgm_notify_wait = cudaEventSynchronize. */
+int dgm_notify_create(void** handle);
+int32_t* dgm_notify_host(void* handle);
+void* dgm_notify_event(void* handle);
+int dgm_notify_wait(void* handle);
+int dgm_notify_destroy(void* handle);
+
 /* ------------------------------------------------------------------------
  * Differentiable 3D-Gaussian rasterizer
  * replaces CudaRasterizer::Rasterizer (dgr/cuda_rasterizer/rasterizer.h:20-86,
@@ -51,6 +62,8 @@ const char* dgm_last_error(void);
                                  rasterizer_impl.cu:281) -- stays on the device */
 #define DGR_ST_OVERFLOW 1     /* 1 if R > R_cap: binning + blend were skipped */
 #define DGR_ST_MAX_TILE 2     /* longest per-tile list (diagnostic) */
+#define DGR_ST_DEPTH_LO 3     /* float bits: smallest / largest view depth of the visible set; */
+#define DGR_ST_DEPTH_HI 4     /* feed them to the next call as depth_hint_lo / depth_hint_hi   */
 
 /* Workspace sizes for P Gaussians, W x H image and room for R_cap
  * (Gaussian, tile) instances.  Mirrors required<GeometryState/ImageState/
@@ -72,7 +85,18 @@ int dgr_workspace_sizes(int P, int W, int H, int64_t R_cap,
  * No host synchronisation: where the reference copies num_rendered to the host
  * (rasterizer_impl.cu:281) this writes it to status[DGR_ST_NUM_RENDERED].  If
  * R exceeds R_cap, status[DGR_ST_OVERFLOW] = 1, out_color is filled with the
- * background and the caller must retry with a larger R_cap. */
+ * background and the caller must retry with a larger R_cap.
+ * Early notification (optional, so that the caller can retry BEFORE anyone consumes
+ * the image -- the drop-in Python layer always does):
+ *   status_host   pinned, device-mapped host memory int32[DGR_STATUS_WORDS] or NULL: the
+ *                 tile-scan kernel stores the status words there as well;
+ *   status_event  cudaEvent_t or NULL: recorded on `stream` right behind the tile scan,
+ *                 i.e. after ~1/5 of the forward -- waiting for it leaves the scatter /
+ *                 sort / blend kernels queued, so the GPU does not idle.
+ * depth_hint_lo < depth_hint_hi (view-depth range of an earlier, similar frame, from
+ * status[DGR_ST_DEPTH_LO/HI]) lets preprocess build the (tile, depth-bucket) histogram
+ * itself (one kernel less); the hint only affects bucket balance, never the result.
+ * Pass 0, 0 when there is none. */
 int dgr_forward(int P, int D, int M,
                 const float* background, int W, int H,
                 const float* means3D, const float* shs, const float* colors_precomp,
@@ -84,7 +108,8 @@ int dgr_forward(int P, int D, int M,
                 void* geom_ws, size_t geom_bytes,
                 void* binning_ws, size_t binning_bytes, int64_t R_cap,
                 void* img_ws, size_t img_bytes,
-                int32_t* status, void* stream);
+                int32_t* status, int32_t* status_host, void* status_event,
+                float depth_hint_lo, float depth_hint_hi, void* stream);
 
 /* Backward: same contract as Rasterizer::backward (rasterizer.h:54-84).  All
  * nine gradient outputs are fully written (zeros for culled Gaussians), the
@@ -109,7 +134,12 @@ int dgr_backward(int P, int D, int M,
 
 /* ------------------------------------------------------------------------
  * Frame batches (data parallelism over training frames): F cameras
- * rendered over ONE set of Gaussians.  No reference counterpart -- the reference renders
+ * rendered over ONE set of Gaussians, or -- what DG-Mesh's dynamic scenes need, where every
+ * frame has its own time and therefore its own deformed means / scales / rotations
+ * (dgmesh/train.py:157-178, gaussian_renderer/__init__.py:60-86) -- over per-frame slabs:
+ * `per_frame` is a mask of DGR_PF_* bits; an input whose bit is set is [F,P,.] (frame f reads
+ * slab f) and its gradient is [F,P,.], written per frame; inputs whose bit is clear are shared
+ * [P,.] and their gradients are SUMMED over the frames.  No reference counterpart -- the reference renders
  * one frame per call (dgmesh/train.py:150-178); this is F x dgr_forward / dgr_backward
  * with (a) one host call, (b) consecutive frames enqueued on alternating internal side
  * streams forked from / joined to `stream`, so the short latency-bound kernels of frame
@@ -124,24 +154,32 @@ int dgr_backward(int P, int D, int M,
  * dL_dmean3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscale[P,3], dL_drot[P,4] summed over
  * frames (fully written, no zero-fill needed).  n_streams: 1..4 side streams.
  * ------------------------------------------------------------------------ */
+#define DGR_PF_MEANS 1
+#define DGR_PF_SCALES 2
+#define DGR_PF_ROTS 4
+#define DGR_PF_OPAC 8
+#define DGR_PF_COLOR 16 /* shs or colors_precomp */
+#define DGR_PF_COV 32
+#define DGR_PF_ALL 63
 int dgr_forward_batch(int F, int P, int D, int M,
                       const float* background, int W, int H,
                       const float* means3D, const float* shs, const float* colors_precomp,
                       const float* opacities, const float* scales, float scale_modifier,
-                      const float* rotations, const float* cov3D_precomp,
+                      const float* rotations, const float* cov3D_precomp, int per_frame,
                       const float* viewmatrices, const float* projmatrices, const float* cam_poses,
                       const float* tan_fovx_host, const float* tan_fovy_host, int prefiltered,
                       float* out_color, int* radii,
                       void* geom_ws, size_t geom_stride,
                       void* binning_ws, size_t binning_stride, int64_t R_cap,
                       void* img_ws, size_t img_stride,
-                      int32_t* status, int n_streams, void* stream);
+                      int32_t* status, int32_t* status_host, void* status_event,
+                      float depth_hint_lo, float depth_hint_hi, int n_streams, void* stream);
 
 int dgr_backward_batch(int F, int P, int D, int M,
                        const float* background, int W, int H,
                        const float* means3D, const float* shs, const float* colors_precomp,
                        const float* scales, float scale_modifier, const float* rotations,
-                       const float* cov3D_precomp,
+                       const float* cov3D_precomp, int per_frame,
                        const float* viewmatrices, const float* projmatrices, const float* cam_poses,
                        const float* tan_fovx_host, const float* tan_fovy_host, const int* radii,
                        void* geom_ws, size_t geom_stride, void* binning_ws, size_t binning_stride,
@@ -277,6 +315,18 @@ typedef struct DglNet {
   const void* Wt1;   /* 32 rows x 256    timenet.2 (256 -> 30), output padded to 32 */
   const void* Wt1T;  /* 256 rows x 32 */
   const float* bt1;  /* [32] */
+  /* Forward precision.  precise != 0 ("bf16x3", what dgl_mlp_pack sets): every forward operand is a
+   * PAIR of bf16 numbers hi + lo (lo = rounding residual) and each layer accumulates
+   * A_hi B_hi + A_lo B_hi + A_hi B_lo in fp32 -- three tcgen05 passes into one TMEM accumulator, ~16
+   * mantissa bits per operand, so activations and ReLU decisions match the reference's fp32 cuBLAS
+   * to ~1e-5 (a single bf16 pass differs by ~2e-3, enough to flip ReLU signs and move the gradients
+   * by ~7 %).  precise == 0: single bf16 pass (3x fewer MMAs).  The backward pass is
+   * bf16 in both modes.  The *lo tables have the layout of W / Wh / Wt0 / Wt1. */
+  int precise;
+  const void* Wlo[8];
+  const void* Whlo;
+  const void* Wt0lo;
+  const void* Wt1lo;
 } DglNet;
 
 typedef struct DglGrads {

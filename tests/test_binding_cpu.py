@@ -37,10 +37,26 @@ def stub(monkeypatch):
     monkeypatch.setattr(_dgm_lib, "lib", lambda: st)
     monkeypatch.setattr(_dgm_lib, "stream_ptr", lambda: 0)
     monkeypatch.setattr(dgr, "_f32c", lambda t, name: None if (t is None or t.numel() == 0) else t.contiguous())
-    # status read-back: pretend R instances, no overflow
-    monkeypatch.setattr(dgr._Workspace, "status_tensor",
-                        lambda self: torch.tensor([st.R, 0, 0, 0, 0, 0, 0, 0], dtype=torch.int32))
-    monkeypatch.setattr(dgr._Sizing, "watch", classmethod(lambda cls, status, key, cap: None))
+    # early notification: pretend R instances per frame, depth range [2, 6]; a frame overflows when the
+    # capacity it was enqueued with is below R (as the tile scan reports it)
+    import struct
+
+    class FakeNotify:
+        host_ptr, event = 0x1000, 0x2000
+
+        def __init__(self):
+            self.words = [0] * (64 * 8)
+
+        def wait(self):
+            last = [c for c in st.calls if c[0] in ("dgr_forward", "dgr_forward_batch")][-1]
+            cap = last[1][26] if last[0] == "dgr_forward" else last[1][28]
+            for f in range(64):
+                self.words[8 * f:8 * f + 5] = [st.R, int(st.R > cap), 0, struct.unpack("i", struct.pack("f", 2.0))[0],
+                                               struct.unpack("i", struct.pack("f", 6.0))[0]]
+
+    fake = FakeNotify()
+    monkeypatch.setattr(dgr._Notify, "get", classmethod(lambda cls, dev: fake))
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
     dgr._Sizing.hint.clear()
     dgr._ws_sizes.clear()
     yield st
@@ -78,13 +94,23 @@ def test_forward_backward_glue(stub, monkeypatch):
     bwd = [c for c in stub.calls if c[0] == "dgr_backward"][0][1]
     for ptr in bwd[24:33]:
         assert ptr is None or ptr % 16 == 0
-    # second call for the same shape reuses the capacity hint (no sizing sync path)
+    # second call for the same shape reuses the capacity and passes the previous frame's depth range as the hint
     n_before = len(stub.calls)
     dgr.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
                                shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
     assert [c[0] for c in stub.calls[n_before:]].count("dgr_forward") == 1
-    cap = [c for c in stub.calls if c[0] == "dgr_forward"][-1][1][26]
-    assert cap == dgr._grow(stub.R) and cap % 32 == 0
+    last = [c for c in stub.calls if c[0] == "dgr_forward"][-1][1]
+    assert last[26] >= dgr._grow(stub.R) and last[26] % 32 == 0
+    assert (last[32], last[33]) == (2.0, 6.0) and last[30] == 0x1000 and last[31] == 0x2000
+    # a frame that does not fit (R grows 100x) is re-run transparently with a larger capacity: two enqueues,
+    # the second into the SAME output tensors, no exception
+    stub.R = 100 * stub.R + 1_000_000
+    n_before = len(stub.calls)
+    color2, _ = dgr.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                           shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+    fw = [c[1] for c in stub.calls[n_before:] if c[0] == "dgr_forward"]
+    assert len(fw) == 2 and fw[1][26] >= stub.R > fw[0][26] and fw[0][20] == fw[1][20] == color2.data_ptr()
+    assert len(dgr._Sizing.hint) == 1
 
 
 def test_precomputed_inputs_and_errors(stub, monkeypatch):
@@ -119,8 +145,6 @@ def test_settings_fields_match_reference_order():
 def test_batch_api_glue(stub, monkeypatch):
     monkeypatch.setattr(dgr, "_sizes", lambda P, W, H, R: (4096, 60 * R + 128, 8192, 4096,
                                                            (60 * R + 128 + 511) // 512 * 512, 8192))
-    monkeypatch.setattr(dgr._BatchWorkspace, "status_tensor",
-                        lambda self: torch.tensor([[stub.R, 0, 0, 0, 0, 0, 0, 0]] * self.F, dtype=torch.int32))
     sc = synth.gaussian_scene(n=48, seed=2)
     cams = [synth.look_at_camera(azimuth_deg=40.0 * k, width=32, height=32) for k in range(3)]
     sets = [synth.raster_settings_for(c, torch.ones(3), settings_cls=dgr.GaussianRasterizationSettings) for c in cams]
@@ -133,11 +157,23 @@ def test_batch_api_glue(stub, monkeypatch):
     color.backward(torch.ones_like(color))
     assert tuple(m2d.grad.shape) == (3, 48, 3) and tuple(leaves["shs"].grad.shape) == (48, 16, 3)
     fwd = [c for c in stub.calls if c[0] == "dgr_forward_batch"][0][1]
-    assert fwd[0] == 3 and fwd[1] == 48 and len(fwd[18]) == 3           # F, P, tan_fovx host array
-    assert fwd[24] % 128 == 0 and fwd[26] % 128 == 0 and fwd[29] % 128 == 0  # workspace strides
+    assert fwd[0] == 3 and fwd[1] == 48 and fwd[15] == 0 and len(fwd[19]) == 3   # F, P, per_frame, tan_fovx array
+    assert fwd[25] % 128 == 0 and fwd[27] % 128 == 0 and fwd[30] % 128 == 0  # workspace strides
     bwd = [c for c in stub.calls if c[0] == "dgr_backward_batch"][0][1]
-    for ptr in bwd[28:36]:
+    for ptr in bwd[29:37]:
         assert ptr is None or ptr % 16 == 0
+    # per-frame deformed means / scales / rotations (DG-Mesh: one time per frame), shared opacity and SH
+    pfl = {k: sc[k][None].repeat(3, 1, 1).clone().requires_grad_(True) for k in ("means3D", "scales", "rotations")}
+    n_before = len(stub.calls)
+    color, _ = dgr.BatchGaussianRasterizer(sets)(means3D=pfl["means3D"], means2D=None, opacities=leaves["opacities"],
+                                                 shs=leaves["shs"], scales=pfl["scales"], rotations=pfl["rotations"])
+    color.backward(torch.ones_like(color))
+    assert [c for c in stub.calls[n_before:] if c[0] == "dgr_forward_batch"][0][1][15] == 1 | 2 | 4
+    assert tuple(pfl["means3D"].grad.shape) == (3, 48, 3) and tuple(pfl["rotations"].grad.shape) == (3, 48, 4)
+    assert tuple(pfl["scales"].grad.shape) == (3, 48, 3)
+    with pytest.raises(ValueError, match="leading dimension"):
+        dgr.BatchGaussianRasterizer(sets)(means3D=pfl["means3D"][:2], means2D=None, opacities=leaves["opacities"],
+                                          shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
     mixed = list(sets)
     mixed[1] = mixed[1]._replace(image_width=48)
     with pytest.raises(ValueError, match="share image size"):

@@ -67,3 +67,29 @@ def test_shard_frames_and_single_process_noop():
     fg = dp.FlatGrad(p)
     (p[0] * 2).sum().backward()
     assert torch.equal(fg.allreduce(), torch.full((3,), 2.0))     # not initialised: no collective
+
+
+def test_flatgrad_survives_zero_grad_set_to_none_and_densification():
+    """the reference loop calls optimizer.zero_grad(set_to_none=True) and densification replaces
+    the Parameter objects; the flat buffer must still hold the true gradients (never a stale / zero one)."""
+    a, b = torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(4))
+    fg = dp.FlatGrad([a, b])
+    opt = torch.optim.SGD([a, b], lr=0.1)
+    (a.sum() * 2 + (b ** 2).sum()).backward()
+    assert torch.equal(fg.allreduce(), torch.cat([torch.full((15,), 2.0), 2 * b.detach()]))
+    opt.zero_grad(set_to_none=True)                     # drops the views
+    assert a.grad is None
+    (a.sum() * 3).backward()                            # autograd allocates a fresh a.grad; b gets none
+    flat = fg.allreduce()
+    assert torch.equal(flat, torch.cat([torch.full((15,), 3.0), torch.zeros(4)]))
+    assert a.grad.data_ptr() == fg.flat.data_ptr()      # re-bound: the next backward accumulates in place
+    a2 = torch.nn.Parameter(torch.randn(9, 3))          # densification: a new, larger parameter
+    fg.params[0] = a2
+    (a2.sum()).backward()
+    import pytest
+    with pytest.raises(RuntimeError, match="rebuild"):
+        fg.allreduce()
+    fg.rebuild([a2, b])
+    fg.zero()
+    (a2.sum()).backward()
+    assert float(fg.allreduce().sum()) == 27.0

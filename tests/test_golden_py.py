@@ -58,19 +58,15 @@ def test_cuda_mlp_matches_reference_golden(path):
     xa = x.clone().requires_grad_(True)
     out = net(xa, t)
     y = torch.cat(out if isinstance(out, tuple) else (out,), -1)
-    assert util.rel_err(y, z["y"]) < 5e-2 and util.rel_l2(y, z["y"]) < 1.5e-2     # bf16 vs fp32
+    # default precision (bf16x3 forward, bf16 backward) against the reference's fp32 CPU results:
+    # outputs <= 1e-4, every gradient <= 3e-2 relative L2 (DESIGN.md "MLP numerics contract")
+    assert util.rel_l2(y, z["y"]) < 1e-4 and util.rel_err(y, z["y"]) < 1e-3
     (y * gout[:, :y.shape[1]]).sum().backward()
-    # gradients of a bf16 chain against the fp32 reference: the rounding of the back-propagated signal
-    # (~0.5 % per tensor, see tests/test_mlp.py for the bound against a bf16 restatement) is amplified by
-    # the positional encoding's derivative (frequencies up to 2^9, heavy cancellation) in dx and in the
-    # first time-net layer, and with only 257 points a handful of ReLU sign flips (bf16 vs fp32
-    # pre-activations) moves the early layers' bias gradients by ~10 % -- measured 6-13 % relative L2.
-    # These bounds only catch gross errors; the tight gradient check is tests/test_mlp.py.
-    assert util.rel_l2(xa.grad, z["dx"]) < 0.2
+    assert util.rel_l2(xa.grad, z["dx"]) < 3e-2
     for k, p in net.named_parameters():
         key = "g_" + k.replace(".", "__")
         if key in z.files:
-            assert util.rel_l2(p.grad, z[key]) < 0.25, k
+            assert util.rel_l2(p.grad, z[key]) < 3e-2, k
 
 
 @pytest.mark.gpu

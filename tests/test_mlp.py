@@ -1,8 +1,13 @@
-"""Deformation / appearance MLPs: the tcgen05 GEMM chain vs (a) a bf16-rounding restatement of the
-reference network (same rounding points as the kernels: bf16 operands, fp32 accumulate) and (b) the
-reference's own fp32 PyTorch modules (oracle/_ref/refpy/time_utils.py).  Tolerances are stated
-relative to each tensor's scale: 2e-3 (L2) / 1e-2 (max) against (a) forward, 2e-2 against (a) backward (the backward
-also rounds dZ to bf16), 5e-2 against the fp32 reference (the bf16 gap, reported)."""
+"""Deformation / appearance MLPs: the tcgen05 GEMM chain vs (a) the reference's own fp32 PyTorch modules
+(oracle/_ref/refpy/time_utils.py) and (b) a bf16-rounding restatement of the reference network (same
+rounding points as the single-pass kernels: bf16 operands, fp32 accumulate).
+
+Contract, relative L2 per tensor:
+  precision 'bf16x3' (default; split-operand forward, bf16 backward): outputs <= 1e-4 and every gradient
+      <= 2e-2 against the fp32 reference (measured ~1e-5 and 0.3-1 %);
+  precision 'bf16' (single pass): outputs 2e-3 / gradients 2e-2 (dx 6e-2) against restatement (b); the gap to
+      the fp32 reference (outputs 5e-2 max, gradients ~7 %: ReLU sign flips) is inherent to one bf16 pass --
+      tests/test_mlp.py::test_single_pass_gap_is_forward_rounding_cpu shows it with no kernel involved."""
 import importlib
 
 import pytest
@@ -75,13 +80,47 @@ def test_emulation_is_close_to_fp32_reference_cpu():
     assert util.rel_err(a, b) < 3e-2
 
 
+@needs_ref
+def test_single_pass_gap_is_forward_rounding_cpu():
+    """Why the default is the split-precision forward: with bf16-rounded FORWARD operands alone (exact fp32
+    backward) the gradients already differ from the fp32 reference by several per cent (ReLU sign flips),
+    while rounding only the back-propagated signal costs ~0.3 %."""
+    torch.manual_seed(1)
+    net = ref.time_utils.DeformNetworkNormal(is_blender=True)
+    x, t = inputs(1500, 3)
+    g = torch.randn(1500, 13, generator=torch.Generator().manual_seed(4))
+
+    def grads(fwd_round):
+        xa = x.clone().requires_grad_(True)
+        if fwd_round:
+            y = torch.cat(heads(net, emulate(net, xa, t)), -1)
+        else:
+            y = torch.cat(net(xa, t), -1)
+        net.zero_grad()
+        y.backward(g)
+        return xa.grad.clone(), net.linear[0].weight.grad.clone()
+
+    dx0, w0 = grads(False)
+    dx1, w1 = grads(True)
+    assert util.rel_l2(dx1, dx0) > 0.03 and util.rel_l2(w1, w0) > 0.03
+
+
 @pytest.mark.gpu
 @needs_ref
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
 @pytest.mark.parametrize("cls,blender,n", [("DeformNetworkNormal", True, 3000), ("DeformNetworkNormal", False, 1000),
                                            ("DeformNetwork", True, 517), ("DeformNetworkNormalSep", True, 2048),
                                            ("AppearanceNetwork", True, 1500), ("DeformNetworkNormal", True, 100_000)])
-def test_mlp_forward_backward(cls, blender, n):
+def test_mlp_forward_backward(cls, blender, n, prec):
     tu = importlib.import_module("utils.time_utils")
+    tu.set_precision(prec)
+    try:
+        _mlp_forward_backward(tu, cls, blender, n, prec)
+    finally:
+        tu.set_precision("bf16x3")
+
+
+def _mlp_forward_backward(tu, cls, blender, n, prec):
     torch.manual_seed(1)
     kw = dict(is_blender=blender)
     mine = getattr(tu, cls)(**kw).cuda()
@@ -98,6 +137,24 @@ def test_mlp_forward_backward(cls, blender, n):
     out = out if isinstance(out, tuple) else (out,)
     ya = torch.cat(out, -1)
     xb = x.clone().requires_grad_(True)
+    g = torch.randn(ya.shape, generator=torch.Generator().manual_seed(4)).cuda()
+    if prec == "bf16x3":
+        # the contract: against the reference's own fp32 modules, forward AND backward
+        yb = theirs(xb, t)
+        yb = torch.cat(yb if isinstance(yb, tuple) else (yb,), -1)
+        assert ya.shape == yb.shape
+        assert util.rel_l2(ya, yb) < 1e-4 and util.rel_err(ya, yb) < 1e-3, "vs fp32 reference"
+        ya.backward(g)
+        yb.backward(g)
+        errs = {"dx": util.rel_l2(xa.grad, xb.grad)}
+        pa, pb = dict(mine.named_parameters()), dict(theirs.named_parameters())
+        for k in pa:
+            assert pa[k].grad is not None and pa[k].grad.shape == pb[k].grad.shape, k
+            errs[k] = util.rel_l2(pa[k].grad, pb[k].grad)
+        print(prec, {k: round(v, 4) for k, v in errs.items()})
+        bad = {k: v for k, v in errs.items() if v > 2e-2}
+        assert not bad, bad
+        return
     yb = torch.cat(heads(theirs, emulate(theirs, xb, t)), -1)
     with torch.no_grad():
         yc = theirs(x, t)
@@ -108,7 +165,6 @@ def test_mlp_forward_backward(cls, blender, n):
     assert util.rel_err(ya, yb) < 1e-2, "vs bf16 restatement (max)"
     assert util.rel_l2(ya, yb) < 2e-3, "vs bf16 restatement (L2)"
     assert util.rel_err(ya, yc) < 5e-2, "vs fp32 reference"
-    g = torch.randn(ya.shape, generator=torch.Generator().manual_seed(4)).cuda()
     ya.backward(g)
     yb.backward(g)
     # gradients: relative L2 per tensor.  dx passes through d pe(x)/dx with frequencies up to 2^9, which

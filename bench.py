@@ -5,12 +5,21 @@ raster fwd+bwd frames/s @ 100k Gaussians, 800x800 (configs[1], SURVEY.md 8(d) C2
   python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path via the C-ABI)
   python bench.py --impl reference --gpus N --steps K ...  # stock diff_gaussian_rasterization (oracle/_ref)
 
-A "step" is one batch of 8 training frames (8 cameras on a ring): at N GPUs each
-rank renders 8/N of them forward+backward and, when N > 1, the canonical-Gaussian gradients
-are combined with ONE NCCL all-reduce over a flat fp32 buffer ("scaling": "strong").
-value = frames / s over the whole job, inputs resident in HBM.  e2e = the same loop through the
-public `GaussianRasterizer` API with the per-frame camera + pixel-gradient uploaded from pinned host
-memory and a gradient checksum read back every frame.
+A "step" is one batch of 8 training frames of a DYNAMIC scene (8 cameras on a ring at times
+t_k = k/8): every frame renders the canonical Gaussians deformed for its own time --
+means3D + d_xyz_k, scales + d_scaling_k, rotations + d_rotation_k, exactly what
+gaussian_renderer.render() hands the rasterizer (dgmesh/gaussian_renderer/__init__.py:60-86) -- so the
+rasterizer sees per-frame [F,P,.] parameters; opacity and SH are shared.  At N GPUs each rank renders
+8/N of the frames forward+backward and, when N > 1, the canonical-Gaussian gradients are combined with
+ONE NCCL all-reduce over a flat fp32 buffer ("scaling": "strong").
+  value         frames/s over the whole job, inputs resident in HBM, through `BatchGaussianRasterizer`
+                (per-frame-parameter frame batch: one call, binning chains overlapped with blend kernels)
+  e2e           the same step fed from pinned HOST buffers every step (cameras + 8-bit ground-truth
+                images up, a gradient checksum down), copies inside the timed region
+  single_frame  the same 8 frames through the reference's own one-frame API (`GaussianRasterizer`,
+                one call per frame), device-timed and e2e -- what an unmodified train.py sees
+The reference arm (--impl reference) runs the same frames with the same per-frame parameters through
+the stock extension's `GaussianRasterizer`.
 """
 import argparse
 import json
@@ -101,8 +110,22 @@ def flat_params(sc, device):
     return leaves, gflat
 
 
-def run_frames(dgr, synth, leaves, cams, dpix, bg, frame_ids, staged=None):
-    """forward + backward of the given frames through the public API.  `staged` (e2e leg) maps a
+def make_deltas(sc, device):
+    """Per-frame deformation of the canonical Gaussians (what the deformation MLP returns for time
+    t_k = k/8): smooth in k, a few per cent of the scene / Gaussian size."""
+    g = torch.Generator().manual_seed(11)
+    P = sc["means3D"].shape[0]
+    base = {"means3D": 0.03 * torch.randn(2, P, 3, generator=g), "scales": 0.001 * torch.randn(2, P, 3, generator=g),
+            "rotations": 0.01 * torch.randn(2, P, 4, generator=g)}
+    out = {}
+    for n, b in base.items():
+        ph = [2 * math.pi * k / FRAMES for k in range(FRAMES)]
+        out[n] = torch.stack([math.cos(a) * b[0] + math.sin(a) * b[1] for a in ph]).to(device).contiguous()
+    return out
+
+
+def run_frames(dgr, synth, leaves, cams, dpix, bg, frame_ids, staged=None, deltas=None):
+    """forward + backward of the given frames through the one-frame public API.  `staged` (e2e leg) maps a
     frame to (event, view, proj, campos, dpix) device tensors filled from pinned host memory by the
     copy stream; the compute stream waits on the frame's event before touching them."""
     last = None
@@ -118,9 +141,14 @@ def run_frames(dgr, synth, leaves, cams, dpix, bg, frame_ids, staged=None):
             bg=bg, scale_modifier=1.0, viewmatrix=view, projmatrix=proj, sh_degree=3, campos=cpos, prefiltered=False,
             debug=False)
         m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
-        color, radii = dgr.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d,
-                                                  opacities=leaves["opacities"], shs=leaves["shs"],
-                                                  scales=leaves["scales"], rotations=leaves["rotations"])
+        if deltas is None:
+            m3, sc_, ro = leaves["means3D"], leaves["scales"], leaves["rotations"]
+        else:   # the frame's own deformed parameters (render(): means3D = xyz + d_xyz, ...)
+            m3 = leaves["means3D"] + deltas["means3D"][k]
+            sc_ = leaves["scales"] + deltas["scales"][k]
+            ro = leaves["rotations"] + deltas["rotations"][k]
+        color, radii = dgr.GaussianRasterizer(rs)(means3D=m3, means2D=m2d, opacities=leaves["opacities"],
+                                                  shs=leaves["shs"], scales=sc_, rotations=ro)
         color.backward(dp(color) if callable(dp) else dp)
         last = color
     return last
@@ -203,13 +231,19 @@ def batch_settings(dgr, cams, bg, frames, views=None, projs=None, campos=None):
     return out
 
 
-def run_batch(dgr, leaves, settings, dpix_stacked, wait_fwd=None):
-    """forward + backward of a frame batch through BatchGaussianRasterizer (this repo's batched API)."""
+def run_batch(dgr, leaves, settings, dpix_stacked, wait_fwd=None, deltas=None):
+    """forward + backward of a frame batch through BatchGaussianRasterizer (this repo's batched API):
+    per-frame deformed means / scales / rotations [F,P,.], shared opacity and SH."""
     if wait_fwd is not None:
         torch.cuda.current_stream().wait_event(wait_fwd)
+    if deltas is None:
+        m3, sc_, ro = leaves["means3D"], leaves["scales"], leaves["rotations"]
+    else:
+        m3 = leaves["means3D"][None] + deltas["means3D"]
+        sc_ = leaves["scales"][None] + deltas["scales"]
+        ro = leaves["rotations"][None] + deltas["rotations"]
     color, radii = dgr.BatchGaussianRasterizer(settings)(
-        means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"], shs=leaves["shs"],
-        scales=leaves["scales"], rotations=leaves["rotations"])
+        means3D=m3, means2D=None, opacities=leaves["opacities"], shs=leaves["shs"], scales=sc_, rotations=ro)
     color.backward(dpix_stacked(color) if callable(dpix_stacked) else dpix_stacked)
     return color
 
@@ -337,11 +371,13 @@ def main():
 
     sc, cams, dpix = make_inputs(dev)
     dpix = [d.to(dev) for d in dpix]
+    deltas_all = make_deltas(sc, dev)
     leaves, gflat = flat_params(sc, dev)
     bg = torch.ones(3, device=dev)
     my_frames = [k for k in range(FRAMES) if k % world == rank]
 
     ours = a.impl == "ours"
+    my_deltas = {n: v[my_frames].contiguous() for n, v in deltas_all.items()}   # this rank's frames, [F_local,P,.]
     if ours:
         dev_settings = batch_settings(dgr, cams, bg, my_frames)
         dpix_stacked = torch.stack([dpix[k] for k in my_frames]).contiguous()
@@ -349,15 +385,21 @@ def main():
     def step():
         gflat.zero_()
         if ours:
-            run_batch(dgr, leaves, dev_settings, dpix_stacked)
+            run_batch(dgr, leaves, dev_settings, dpix_stacked, deltas=my_deltas)
         else:
-            run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames)
+            run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, deltas=deltas_all)
         if world > 1:
             dist.all_reduce(gflat)  # the one collective of the step
 
     def step_render_only():
         gflat.zero_()
-        run_batch(dgr, leaves, dev_settings, dpix_stacked)
+        run_batch(dgr, leaves, dev_settings, dpix_stacked, deltas=my_deltas)
+
+    def step_single():      # the same frames, one GaussianRasterizer call each (reference-style loop)
+        gflat.zero_()
+        run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, deltas=deltas_all)
+        if world > 1:
+            dist.all_reduce(gflat)
 
     # Optional: capture the step once and replay it as a CUDA graph (parameters, cameras and pixel
     # gradients live at fixed addresses exactly as in a training loop with in-place optimiser updates;
@@ -407,11 +449,11 @@ def main():
         feed.upload()
         gflat.zero_()
         if ours:
-            run_batch(dgr, leaves, feed_settings, feed.pixel_grad, wait_fwd=feed.ev_cam)
+            run_batch(dgr, leaves, feed_settings, feed.pixel_grad, wait_fwd=feed.ev_cam, deltas=my_deltas)
         else:
             staged = {k: (feed.ev_cam, feed.views[i], feed.projs[i], feed.campos[i],
                           (lambda c, i=i: feed.pixel_grad(c, i))) for i, k in enumerate(my_frames)}
-            run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged)
+            run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged, deltas=deltas_all)
         if world > 1:
             dist.all_reduce(gflat)
         feed.finish(gflat.sum())
@@ -421,6 +463,29 @@ def main():
     host_results = feed.drain()
     assert len(host_results) == e2e_steps + 3 and all(math.isfinite(v) for v in host_results), host_results
     e2e_value = FRAMES * e2e_steps / (ms_e2e * 1e-3)
+
+    single = None
+    if ours:
+        # ---- the reference's own one-frame API: device-timed, then fed from the host like e2e
+        ms_single = timed(step_single, a.steps, 3, world)
+        feed1 = HostFeed(cams, my_frames, dev)
+
+        def step_single_e2e():
+            feed1.upload()
+            gflat.zero_()
+            staged = {k: (feed1.ev_cam, feed1.views[i], feed1.projs[i], feed1.campos[i],
+                          (lambda c, i=i: feed1.pixel_grad(c, i))) for i, k in enumerate(my_frames)}
+            run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged, deltas=deltas_all)
+            if world > 1:
+                dist.all_reduce(gflat)
+            feed1.finish(gflat.sum())
+
+        ms_single_e2e = timed(step_single_e2e, a.steps, 3, world)
+        feed1.drain()
+        single = {"api": "GaussianRasterizer, one call per frame (reference API)",
+                  "value": FRAMES * a.steps / (ms_single * 1e-3), "unit": "frames/s",
+                  "ms_per_frame": ms_single / a.steps / len(my_frames),
+                  "e2e": {"value": FRAMES * a.steps / (ms_single_e2e * 1e-3), "unit": "frames/s"}}
     h2d = feed.h2d_bytes * world
     d2h = 4 * world
 
@@ -432,7 +497,8 @@ def main():
                                "step = 8-frame batch (8 ring cameras), frames sharded over ranks",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "frames_per_step": FRAMES,
                    "parallelism": f"dp{world} over frames" + (", 1 NCCL all-reduce of grads" if world > 1 else ""),
-                   "api": ("BatchGaussianRasterizer (frame batch, in-kernel gradient accumulation)"
+                   "scene": "dynamic: frame k renders xyz + d_xyz_k, scales + d_scaling_k, rotations + d_rotation_k",
+                   "api": ("BatchGaussianRasterizer (frame batch, per-frame deformed means/scales/rotations)"
                            + (", step replayed as one CUDA graph" if (ours and use_graph) else "")) if ours
                           else "GaussianRasterizer per frame (reference API)",
                    "l2_policy": "inputs larger than L2: per step 8 frames x (~42 MB instance records + 12 MB "
@@ -441,6 +507,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "clocks": clocks,
     }
+    if single:
+        out["single_frame"] = single
     if breakdown:
         out["breakdown"] = breakdown
     if graph_note:
@@ -462,7 +530,7 @@ def main():
         nprof = 3
         for _ in range(nprof):
             for k in my_frames:
-                run_frames(dgr, synth, leaves, cams, dpix, bg, [k])
+                run_frames(dgr, synth, leaves, cams, dpix, bg, [k], deltas=deltas_all)
                 for n, v in _dgm_lib.profile_read().items():
                     acc[n] = acc.get(n, 0.0) + v
         _dgm_lib.lib().dgm_profile_enable(0)
@@ -473,8 +541,10 @@ def main():
         for k in my_frames:
             c = cams[k]
             rs = synth.raster_settings_for(c, bg, settings_cls=dgr.GaussianRasterizationSettings)
-            R, *_ = dgr._C.rasterize_gaussians(bg, sc["means3D"], torch.Tensor([]), sc["opacities"], sc["scales"],
-                                               sc["rotations"], 1.0, torch.Tensor([]), rs.viewmatrix, rs.projmatrix,
+            R, *_ = dgr._C.rasterize_gaussians(bg, sc["means3D"] + deltas_all["means3D"][k], torch.Tensor([]),
+                                               sc["opacities"], sc["scales"] + deltas_all["scales"][k],
+                                               sc["rotations"] + deltas_all["rotations"][k], 1.0, torch.Tensor([]),
+                                               rs.viewmatrix, rs.projmatrix,
                                                rs.tanfovx, rs.tanfovy, HEIGHT, WIDTH, sc["shs"], 3, rs.campos, False,
                                                False)
             Rs.append(R)
@@ -501,7 +571,9 @@ def main():
                                    "40 B instance record), not HBM-bound: see DESIGN.md 'roofline'"}
         out["kernel_ms"] = kern_ms
         out["num_rendered_mean"] = R_mean
-        out["gpu_launches"] = 8 * len(my_frames) * a.steps * world
+        # this library's kernels per frame: preprocess(+count), tile_scan, scatter, sort_pack, render_fwd,
+        # render_bwd, preprocess_bwd (torch's own elementwise kernels around them are not counted)
+        out["gpu_launches"] = 7 * len(my_frames) * a.steps * world
         if rank == 0 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_port()
             try:

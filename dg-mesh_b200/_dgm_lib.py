@@ -61,6 +61,10 @@ SIGNATURES = {
     "dgl_mlp_workspace": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "dgl_mlp_forward": (c_int, [P, c_int, P, P, P, c_int, P, c_size_t, P]),
     "dgl_mlp_backward": (c_int, [P, c_int, P, P, P, P, c_size_t, P, P, P]),
+    "dgd_workspace_size": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
+    "dgd_plan": (c_int, [c_int, P, P, P, P, c_float, c_float, c_float, c_float, c_int, c_float, P, c_size_t, P, P]),
+    "dgd_split_stds": (c_int, [c_int, P, P, c_size_t, P, P]),
+    "dgd_apply": (c_int, [c_int, c_int, P, P, P, P, c_size_t, P]),
     "dgm_profile_enable": (c_int, [c_int]),
     "dgloss_workspace_size": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "dgloss_forward": (c_int, [c_int, c_int, P, P, c_float, c_int, P, P, c_size_t, P]),
@@ -101,6 +105,12 @@ class DglRaw(ctypes.Structure):
 class DglRawGrads(ctypes.Structure):
     _fields_ = [("W", c_void_p * 8), ("b", c_void_p * 8), ("Wh", c_void_p * 4), ("bh", c_void_p * 4),
                 ("Wt0", c_void_p), ("bt0", c_void_p), ("Wt1", c_void_p), ("bt1", c_void_p)]
+
+
+class DgdField(ctypes.Structure):
+    """Mirror of `struct DgdField` (densify_and_prune gather)."""
+    _fields_ = [("src", c_void_p), ("m1_src", c_void_p), ("m2_src", c_void_p), ("dst", c_void_p),
+                ("m1_dst", c_void_p), ("m2_dst", c_void_p), ("width", c_int), ("role", c_int)]
 
 
 class DglGrads(ctypes.Structure):

@@ -7,6 +7,7 @@
 #include "mc_kernels.h"
 #include "loss_kernels.h"
 #include "mlp_kernels.h"
+#include "densify_kernels.h"
 
 #include <string.h>
 #include <stdlib.h>
@@ -28,10 +29,13 @@ int bad(const char* msg) {
 
 namespace dgm {
 Profiler g_prof;
-// programmatic dependent launch between the rasterizer's kernels (DGMESH_B200_PDL=0 turns it off)
+// programmatic dependent launch between the rasterizer's kernels: DGMESH_B200_PDL=1 turns it on.
+// Off by default: measured on B200 (profiles/r2_pdl_ab.json) it is 2-3 % SLOWER for this chain --
+// early-resident dependents hold CTA slots / shared memory while the predecessor's tail is still
+// running, and the launch gaps it could hide total only ~30 us of a 440 us frame.
 int g_pdl = [] {
   const char* e = getenv("DGMESH_B200_PDL");
-  return (e && e[0] == '0') ? 0 : 1;
+  return (e && e[0] == '1') ? 1 : 0;
 }();
 // ---- state export (parity tests): rebuild the reference-visible views from the
 // private workspaces.  point_list_keys is reconstructed as (tile << 32 | depth bits),
@@ -640,6 +644,62 @@ int dgloss_backward(int H, int W, const float* img, const float* gt, float lambd
     return DGM_E_WORKSPACE;
   }
   return check(dgm::launch_loss_backward(H, W, img, gt, lambda_dssim, mode, dL_dloss, dL_dimg, ws, (cudaStream_t)stream));
+}
+
+int dgd_workspace_size(int P, size_t* bytes) {
+  if (P <= 0 || !bytes) return bad("dgd_workspace_size: bad argument");
+  *bytes = dgm::densify_ws_bytes(P);
+  return DGM_OK;
+}
+
+static int dgd_check(int P, const void* ws, size_t ws_bytes) {
+  if (P <= 0 || !ws) return bad("densify: bad argument");
+  if (ws_bytes < dgm::densify_ws_bytes(P)) {
+    strncpy(g_last_error, "densify: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return DGM_OK;
+}
+
+int dgd_plan(int P, const float* xyz_gradient_accum, const float* denom, const float* scaling_raw,
+             const float* opacity_raw, float max_grad, float min_opacity, float extent, float percent_dense,
+             int size_prune, float max_screen_size, void* ws, size_t ws_bytes, int32_t* counts, void* stream) {
+  int rc = dgd_check(P, ws, ws_bytes);
+  if (rc != DGM_OK) return rc;
+  if (!xyz_gradient_accum || !denom || !scaling_raw || !opacity_raw || !counts) return bad("dgd_plan: null pointer");
+  return check(dgm::launch_densify_plan(P, xyz_gradient_accum, denom, scaling_raw, opacity_raw, max_grad, min_opacity,
+                                        extent, percent_dense, size_prune, max_screen_size, ws, counts,
+                                        (cudaStream_t)stream));
+}
+
+int dgd_split_stds(int P, const float* scaling_raw, void* ws, size_t ws_bytes, float* stds, void* stream) {
+  int rc = dgd_check(P, ws, ws_bytes);
+  if (rc != DGM_OK) return rc;
+  if (!scaling_raw || !stds) return bad("dgd_split_stds: null pointer");
+  return check(dgm::launch_densify_stds(P, scaling_raw, ws, stds, (cudaStream_t)stream));
+}
+
+int dgd_apply(int P, int n_fields, const DgdField* fields_host, const float* rotation_raw, const float* samples,
+              void* ws, size_t ws_bytes, void* stream) {
+  int rc = dgd_check(P, ws, ws_bytes);
+  if (rc != DGM_OK) return rc;
+  if (n_fields < 1 || n_fields > DGD_MAX_FIELDS || !fields_host || !rotation_raw) return bad("dgd_apply: bad argument");
+  dgm::DensifyTables t = {};
+  t.n_fields = n_fields;
+  t.rotation_raw = rotation_raw;
+  int cols = 0;
+  for (int i = 0; i < n_fields; ++i) {
+    const DgdField& f = fields_host[i];
+    if (!f.src || !f.dst || f.width < 1 || ((f.m1_src == nullptr) != (f.m1_dst == nullptr)) ||
+        ((f.m1_src == nullptr) != (f.m2_src == nullptr)) || ((f.m1_dst == nullptr) != (f.m2_dst == nullptr)))
+      return bad("dgd_apply: bad field");
+    t.f[i].src = f.src; t.f[i].m1_src = f.m1_src; t.f[i].m2_src = f.m2_src;
+    t.f[i].dst = f.dst; t.f[i].m1_dst = f.m1_dst; t.f[i].m2_dst = f.m2_dst;
+    t.f[i].width = f.width; t.f[i].role = f.role;
+    cols += f.width;
+  }
+  if (cols > 64) return bad("dgd_apply: more than 64 parameter columns");
+  return check(dgm::launch_densify_apply(P, t, samples, ws, (cudaStream_t)stream));
 }
 
 // ---- early notification objects: an event + a device-mapped pinned status mirror.  These are the

@@ -21,15 +21,16 @@ if _root not in sys.path:
     sys.path.insert(0, _root)
 import _dgm_lib  # noqa: E402
 
-_plans = {}  # G -> (plan handle, workspace bytes)
+_plans = {}  # (device index, G) -> (plan handle, workspace bytes): cuFFT plans belong to a device
 
 
 def _plan(G):
-    if G not in _plans:
+    key = (torch.cuda.current_device(), G)
+    if key not in _plans:
         h, nbytes = ctypes.c_void_p(), _dgm_lib.c_size_t()
         _dgm_lib.check(_dgm_lib.lib().dgp_plan_create(G, ctypes.byref(h), ctypes.byref(nbytes)), "dgp_plan_create")
-        _plans[G] = (h, nbytes.value)
-    return _plans[G]
+        _plans[key] = (h, nbytes.value)
+    return _plans[key]
 
 
 class _DPSRFunction(torch.autograd.Function):

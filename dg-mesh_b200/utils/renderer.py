@@ -105,3 +105,27 @@ def mesh_renderer(glctx, gaussians, d_xyz, d_normal, fid, deform_back, appearanc
     mask = render_mask(glctx, verts, faces, pose, K, resolution=res)[..., [0]]
     mesh_image = render_mesh(glctx, verts, faces, vtx_color, pose, K, resolution=res, whitebackground=whitebackground)
     return mask, mesh_image, verts, faces, vtx_color
+
+
+def __getattr__(name):
+    """Names this drop-in does not define (`mesh_shape_renderer`, `pointcloud_renderer`: PyTorch3D /
+    matplotlib visualisation helpers used by render_test.py / render_trajectory.py, outside the hot
+    path) resolve to the reference's own `utils/renderer.py`, found through the merged `utils` package
+    path that launch.install() sets up (this directory first, the reference's second)."""
+    import importlib.util
+    import os
+    import sys
+    pkg = sys.modules.get("utils")
+    here = os.path.dirname(os.path.abspath(__file__))
+    for d in list(getattr(pkg, "__path__", [])):
+        cand = os.path.join(d, "renderer.py")
+        if os.path.abspath(d) != here and os.path.exists(cand):
+            mod = sys.modules.get("_reference_utils_renderer")
+            if mod is None:
+                spec = importlib.util.spec_from_file_location("_reference_utils_renderer", cand)
+                mod = importlib.util.module_from_spec(spec)
+                sys.modules["_reference_utils_renderer"] = mod
+                spec.loader.exec_module(mod)
+            if hasattr(mod, name):
+                return getattr(mod, name)
+    raise AttributeError(f"module 'utils.renderer' has no attribute {name!r}")

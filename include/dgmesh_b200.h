@@ -391,6 +391,43 @@ int dgloss_backward(int H, int W, const float* img, const float* gt, float lambd
                     const float* dL_dloss, float* dL_dimg, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Adaptive density control on the device (next-tier row SURVEY.md 8(f)-2): the whole of
+ * GaussianModelDPSRDynamicAnchor.densify_and_prune
+ * (dgmesh/scene/gaussian_model_dpsr_dynamic_anchor.py:469-551: densify_and_clone, densify_and_split
+ * with N = 2, prune; built on cat_tensors_to_optimizer :403-428, _prune_optimizer :383-401,
+ * densification_postfix :430-452) as one plan and one gather over the seven parameter tensors and
+ * both Adam moments.  Same survivors, same final row order
+ * [kept originals | clones | first split copies | second split copies], same values.
+ *   dgd_plan        xyz_gradient_accum[P], denom[P], _scaling[P,3], _opacity[P] (raw, pre-activation)
+ *                   -> counts[4] on the device = {kept originals, clones, split-selected, children per copy};
+ *                   the new model has counts[0] + counts[1] + 2 * counts[3] rows.  size_prune = the
+ *                   reference's `if max_screen_size:` branch.  The caller reads counts (the one host read).
+ *   dgd_split_stds  stds[2 * counts[2], 3] = get_scaling[selected].repeat(2, 1): feed torch.normal(0, stds)
+ *                   so the generator is consumed exactly as by the reference (:463-465)
+ *   dgd_apply       fields_host: up to DGD_MAX_FIELDS tensors [P, width] with optional Adam moments,
+ *                   role 1 = xyz, 2 = _scaling, 0 = copied as is; samples[2 * counts[2], 3];
+ *                   rotation_raw[P,4].  Writes every row of every output tensor.
+ * ------------------------------------------------------------------------ */
+#define DGD_MAX_FIELDS 8
+typedef struct DgdField {
+  const float* src;     /* [P, width] */
+  const float* m1_src;  /* Adam exp_avg    [P, width] or NULL */
+  const float* m2_src;  /* Adam exp_avg_sq [P, width] or NULL */
+  float* dst;           /* [n_out, width] */
+  float* m1_dst;
+  float* m2_dst;
+  int width;
+  int role;             /* 0 plain, 1 xyz, 2 scaling */
+} DgdField;
+int dgd_workspace_size(int P, size_t* bytes);
+int dgd_plan(int P, const float* xyz_gradient_accum, const float* denom, const float* scaling_raw,
+             const float* opacity_raw, float max_grad, float min_opacity, float extent, float percent_dense,
+             int size_prune, float max_screen_size, void* ws, size_t ws_bytes, int32_t* counts, void* stream);
+int dgd_split_stds(int P, const float* scaling_raw, void* ws, size_t ws_bytes, float* stds, void* stream);
+int dgd_apply(int P, int n_fields, const DgdField* fields_host, const float* rotation_raw, const float* samples,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * Measurement hooks (bench.py roofline leg).  Off by default.  When enabled the
  * library records a CUDA event pair around each of its kernels ON THE LAUNCHING
  * STREAM; dgm_profile_read synchronises those events (the only call in this

@@ -19,6 +19,8 @@ and, as the equivalent of `pip install --target` (build OUTPUT, git-ignored):
   oracle/_ref/diff_gaussian_rasterization/__init__.py   (the reference Python surface)
   oracle/_ref/refpy/{time_utils,rigid_utils,dpsr,dpsr_utils,graphics_utils}.py
         (pure-PyTorch reference modules used as MLP / DPSR / camera oracles)
+  oracle/_ref/dgmesh/        the reference's whole Python tree minus submodules/ (train.py, scene/,
+        utils/, arguments/, configs/): what tools/train_harness.py runs UNMODIFIED
 
 The reference ships no sm_100 build; it needs two forced includes under gcc 13
 (`<cstdint>` for rasterizer_impl.h, `<cfloat>` for simple_knn.cu) -- passed on
@@ -88,6 +90,13 @@ def build(force=False):
         ("dgmesh/nvdiffrast_utils/dpsr_utils.py", "dpsr_utils.py"),
     ]:
         shutil.copyfile(os.path.join(REF, src), os.path.join(refpy, dst))
+    # the reference's Python tree (train.py, scene/, utils/, arguments/, configs/ ...) for the
+    # "unmodified train.py" harness (tools/train_harness.py); build output, git-ignored like the rest
+    tree = os.path.join(OUT, "dgmesh")
+    if os.path.isdir(tree):
+        shutil.rmtree(tree)
+    shutil.copytree(os.path.join(REF, "dgmesh"), tree,
+                    ignore=shutil.ignore_patterns("submodules", "__pycache__", "*.so", "*.o", ".git*"))
     # remove ninja build litter (objects) to keep the snapshot small
     for d in (dgr_out, knn_out):
         for fn in os.listdir(d):

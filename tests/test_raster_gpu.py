@@ -277,16 +277,18 @@ def test_unmodified_loop_survives_growing_R_without_exception():
     ref = util.load_reference_rasterizer()
     if ref is None:
         pytest.skip("reference extension not built")
-    sc, _ = util.small_scene(n=3000, W=128, H=96, seed=4, scale=0.03)
+    sc, _ = util.small_scene(n=3000, W=128, H=96, seed=4, scale=0.12)
     sc = _cuda(sc)
     bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
     dgr._Sizing.hint.clear()
     dgr._Sizing.hint[(torch.cuda.current_device(), 128, 96)] = [32, 0.0, 0.0]     # far too small to start with
     Rs, replays = [], 0
-    for it, radius in enumerate((9.0, 6.0, 4.0, 2.5, 1.6, 4.0)):                 # zooming in: R grows > 4x
+    for it, radius in enumerate((14.0, 8.0, 5.0, 3.0, 2.0, 5.0)):                # zooming in: R grows > 4x
         cam = _cam_cuda(synth.look_at_camera(azimuth_deg=30.0 * it, elevation_deg=10.0, radius=radius, width=128,
                                              height=96, fovx=0.6911, fovy=0.6911 * 96 / 128))
         dpix = torch.randn(3, 96, 128, generator=torch.Generator().manual_seed(it)).cuda()
+        # no head-room: the workspace is exactly what the PREVIOUS camera needed, so every zoom-in overflows
+        dgr._Sizing.hint[(torch.cuda.current_device(), 128, 96)][0] = max(32, Rs[-1] if Rs else 0)
         cap_before = dgr._Sizing.hint[(torch.cuda.current_device(), 128, 96)][0]
         a = run_ours(sc, cam, bg, dpix=dpix)
         b = run_ref(sc, cam, bg, dpix=dpix)
@@ -297,7 +299,7 @@ def test_unmodified_loop_survives_growing_R_without_exception():
         assert util.rel_err(a["color"], b["color"]) < TOL, (it, "color")
         for k in ("means3D", "opacities", "scales", "rotations", "shs", "means2D"):
             assert util.rel_err(a["grads"][k], b["grads"][k]) < TOL, (it, k)
-    assert max(Rs) > 4 * min(Rs) and replays >= 2, (Rs, replays)
+    assert max(Rs) > 4 * min(Rs) and replays >= 4, (Rs, replays)
 
 
 def test_depth_hint_changes_nothing():

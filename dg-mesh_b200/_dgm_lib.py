@@ -61,6 +61,12 @@ SIGNATURES = {
     "dgl_mlp_workspace": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "dgl_mlp_forward": (c_int, [P, c_int, P, P, P, c_int, P, c_size_t, P]),
     "dgl_mlp_backward": (c_int, [P, c_int, P, P, P, P, c_size_t, P, P, P]),
+    "dgmr_rasterize": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "dgmr_rasterize_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P]),
+    "dgmr_interpolate": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
+    "dgmr_interpolate_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "dgmr_antialias": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "dgmr_antialias_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "dgd_workspace_size": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
     "dgd_plan": (c_int, [c_int, P, P, P, P, c_float, c_float, c_float, c_float, c_int, c_float, P, c_size_t, P, P]),
     "dgd_split_stds": (c_int, [c_int, P, P, c_size_t, P, P]),

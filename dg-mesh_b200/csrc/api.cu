@@ -8,6 +8,7 @@
 #include "loss_kernels.h"
 #include "mlp_kernels.h"
 #include "densify_kernels.h"
+#include "meshrast_kernels.h"
 
 #include <string.h>
 #include <stdlib.h>
@@ -644,6 +645,42 @@ int dgloss_backward(int H, int W, const float* img, const float* gt, float lambd
     return DGM_E_WORKSPACE;
   }
   return check(dgm::launch_loss_backward(H, W, img, gt, lambda_dssim, mode, dL_dloss, dL_dimg, ws, (cudaStream_t)stream));
+}
+
+int dgmr_rasterize(int V, int F, int W, int H, const float* pos, const int32_t* tri, void* zbuf, float* rast,
+                   void* stream) {
+  if (V < 0 || F < 0 || W <= 0 || H <= 0 || !zbuf || !rast || (F > 0 && (!pos || !tri)))
+    return bad("dgmr_rasterize: bad argument");
+  return check(dgm::launch_mr_rasterize(V, F, W, H, pos, tri, zbuf, rast, (cudaStream_t)stream));
+}
+int dgmr_rasterize_bwd(int W, int H, const float* rast, const int32_t* tri, const float* pos, const float* grast,
+                       float* gpos, void* stream) {
+  if (W <= 0 || H <= 0 || !rast || !tri || !pos || !grast || !gpos) return bad("dgmr_rasterize_bwd: bad argument");
+  return check(dgm::launch_mr_rasterize_bwd(W, H, rast, tri, pos, grast, gpos, (cudaStream_t)stream));
+}
+int dgmr_interpolate(int W, int H, int C, const float* attr, const float* rast, const int32_t* tri, float* out,
+                     void* stream) {
+  if (W <= 0 || H <= 0 || C < 1 || !attr || !rast || !tri || !out) return bad("dgmr_interpolate: bad argument");
+  return check(dgm::launch_mr_interpolate(W, H, C, attr, rast, tri, out, (cudaStream_t)stream));
+}
+int dgmr_interpolate_bwd(int W, int H, int C, const float* attr, const float* rast, const int32_t* tri,
+                         const float* gout, float* gattr, float* grast, void* stream) {
+  if (W <= 0 || H <= 0 || C < 1 || !attr || !rast || !tri || !gout) return bad("dgmr_interpolate_bwd: bad argument");
+  return check(dgm::launch_mr_interpolate_bwd(W, H, C, attr, rast, tri, gout, gattr, grast, (cudaStream_t)stream));
+}
+int dgmr_antialias(int W, int H, int C, const float* color, const float* rast, const float* pos,
+                   const int32_t* tri, const int32_t* opp, float* out, void* stream) {
+  if (W <= 0 || H <= 0 || C < 1 || !color || !rast || !pos || !tri || !opp || !out)
+    return bad("dgmr_antialias: bad argument");
+  return check(dgm::launch_mr_antialias(W, H, C, color, rast, pos, tri, opp, out, (cudaStream_t)stream));
+}
+int dgmr_antialias_bwd(int W, int H, int C, const float* color, const float* rast, const float* pos,
+                       const int32_t* tri, const int32_t* opp, const float* gout, float* gcolor, float* gpos,
+                       void* stream) {
+  if (W <= 0 || H <= 0 || C < 1 || !color || !rast || !pos || !tri || !opp || !gout)
+    return bad("dgmr_antialias_bwd: bad argument");
+  return check(dgm::launch_mr_antialias_bwd(W, H, C, color, rast, pos, tri, opp, gout, gcolor, gpos,
+                                            (cudaStream_t)stream));
 }
 
 int dgd_workspace_size(int P, size_t* bytes) {

@@ -12,8 +12,9 @@ would be replaced).  `install()` therefore fixes the resolution order BEFORE the
     path lists THIS package's directory first and the reference's second: `utils.time_utils`,
     `utils.renderer`, `utils.loss_utils`, `nvdiffrast_utils.dpsr` resolve here, every other submodule
     (`utils.general_utils`, `nvdiffrast_utils.regularizer`, ...) falls through to the reference;
-  * `gaussian_renderer`, `diff_gaussian_rasterization`, `simple_knn`, `diso` are imported from here and
-    pinned in sys.modules;
+  * `gaussian_renderer`, `diff_gaussian_rasterization`, `simple_knn`, `diso` and `nvdiffrast` (the CUDA
+    triangle rasteriser that stands in for the third-party package) are imported from here and pinned in
+    sys.modules;
   * once the reference's `scene` package is imported, `GaussianModelDPSRDynamicAnchor.densify_and_prune`
     is replaced by the fused device version (densify.py).
 
@@ -28,7 +29,8 @@ import types
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 _MERGED = ("utils", "nvdiffrast_utils")
-_PINNED = ("diff_gaussian_rasterization", "simple_knn", "simple_knn._C", "diso", "gaussian_renderer")
+_PINNED = ("diff_gaussian_rasterization", "simple_knn", "simple_knn._C", "diso", "gaussian_renderer", "nvdiffrast",
+           "nvdiffrast.torch")
 
 
 def _merged_package(name, dirs):

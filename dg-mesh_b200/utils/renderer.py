@@ -1,56 +1,77 @@
-"""Drop-in `utils.renderer.mesh_renderer` (reference: dgmesh/utils/renderer.py:124-233):
-Gaussians -> DPSR indicator grid -> marching cubes -> per-vertex colour, i.e. the mesh-extraction part
-of the hot path.  Same signature, same return values.
+"""Drop-in `utils.renderer` (reference: dgmesh/utils/renderer.py:33-233): Gaussians -> DPSR indicator grid ->
+marching cubes -> per-vertex colour -> mesh rasterisation (mask + image), i.e. the whole mesh branch of the
+training step.  Same signatures, same return values.
 
 What changes underneath: DPSR and marching cubes are the sm_100a kernels of this package; when
-`gaussians.dpsr` is this package's DPSR, the sign fix + threshold that follow the solve
-(reference :163-168) are fused into it, which removes the host read of psr[0,0,0,0].
-The mesh RASTERISATION at the end (`render_mask` / `render_mesh`, reference :33-121) is nvdiffrast, a
-third-party OpenGL/CUDA rasteriser outside this round's scope: with
-`viewpoint_cam is None` (dynamic-mesh export, train.py:403,447) nothing else is needed; with a
-camera, nvdiffrast is imported lazily and used exactly as the reference does."""
+`gaussians.dpsr` is this package's DPSR, the sign fix + threshold that follow the solve (reference
+:163-168) are fused into it, which removes the host read of psr[0,0,0,0].  The mesh RASTERISATION
+(`render_mask` / `render_mesh`, reference :33-121: nvdiffrast's rasterize / interpolate / antialias on an
+OpenGL context) runs on this package's CUDA triangle rasteriser (`nvdiffrast.torch` here is
+dg-mesh_b200/nvdiffrast -> meshrast.py): no GL context, and `mesh_renderer` rasterises the mesh ONCE for the
+mask and the image (the reference rasterises it twice)."""
 import torch
+
+import nvdiffrast.torch as dr
 
 SMALL_NUMBER = 1e-6
 
-
-def _nvdiffrast():
-    try:
-        import nvdiffrast.torch as dr
-        from nvdiffrast_utils import util
-    except Exception as e:  # pragma: no cover - depends on the deployment
-        raise RuntimeError("mesh_renderer(viewpoint_cam=...) needs nvdiffrast (mesh rasterisation is outside the "
-                           "B200 hot path; see INTEGRATION.md)") from e
-    return dr, util
+# camera-convention changes of dgmesh/nvdiffrast_utils/util.py:470-475 (the reference module itself imports the
+# third-party nvdiffrast and imageio packages at import time, so the constants are restated here)
+_B2CV = ((1.0, 0.0, 0.0, 0.0), (0.0, -1.0, 0.0, 0.0), (0.0, 0.0, -1.0, 0.0), (0.0, 0.0, 0.0, 1.0))
 
 
-def render_mask(glctx, mesh_v_pos, mesh_t_pos_idx, pose, K, resolution=[800, 800]):
-    """reference :33-66"""
-    dr, util = _nvdiffrast()
-    proj = util.K_to_projection(K, resolution[0], resolution[1])
-    v_pos_clip = util.transform_pos(proj @ pose, mesh_v_pos)
+def _blender2opencv(device):
+    return torch.tensor(_B2CV, dtype=torch.float32, device=device)
+
+
+def K_to_projection(K, H, W, n=0.001, f=10.0):
+    """nvdiffrast_utils/util.py:484-490 (argument names as there: it is called with (K, height, width))."""
+    fu, fv, cu, cv = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    return torch.tensor([[2 * fu / W, 0, -2 * cu / W + 1, 0], [0, 2 * fv / H, 2 * cv / H - 1, 0],
+                         [0, 0, -(f + n) / (f - n), -2 * f * n / (f - n)], [0, 0, -1, 0]],
+                        dtype=torch.float32, device=K.device)
+
+
+def transform_pos(mtx, pos):
+    """(x, y, z) -> (x, y, z, 1) @ mtx^T, [1, N, 4] (nvdiffrast_utils/util.py:493-497)."""
+    posw = torch.cat([pos, torch.ones([pos.shape[0], 1], device=pos.device)], axis=1)
+    return torch.matmul(posw, mtx.t())[None, ...]
+
+
+def _raster(glctx, mesh_v_pos, mesh_t_pos_idx, pose, K, resolution):
+    proj = K_to_projection(K, resolution[0], resolution[1])
+    v_pos_clip = transform_pos(proj @ pose, mesh_v_pos)
     rast_out, _ = dr.rasterize(glctx, v_pos_clip, mesh_t_pos_idx, resolution=resolution)
+    topo = dr.edge_opposites(mesh_t_pos_idx, mesh_v_pos.shape[0]) if mesh_t_pos_idx.shape[0] else None
+    return v_pos_clip, rast_out, topo
+
+
+def _mask_from(rast_out, v_pos_clip, mesh_v_pos, mesh_t_pos_idx, topo):
     vtx_color = torch.ones(mesh_v_pos.shape, dtype=torch.float, device=v_pos_clip.device)
     color, _ = dr.interpolate(vtx_color[None, ...], rast_out, mesh_t_pos_idx)
-    color = dr.antialias(color, rast_out, v_pos_clip, mesh_t_pos_idx)
+    color = dr.antialias(color, rast_out, v_pos_clip, mesh_t_pos_idx, topology_hash=topo)
     return torch.flip(color[0, :, :], dims=[0])
 
 
-def render_mesh(glctx, mesh_v_pos, mesh_t_pos_idx, vtx_color, pose, K, resolution=[800, 800], whitebackground=False):
-    """reference :69-121"""
-    dr, util = _nvdiffrast()
-    proj = util.K_to_projection(K, resolution[0], resolution[1])
-    v_pos_clip = util.transform_pos(proj @ pose, mesh_v_pos)
-    rast_out, _ = dr.rasterize(glctx, v_pos_clip, mesh_t_pos_idx, resolution=resolution)
+def _image_from(rast_out, v_pos_clip, mesh_t_pos_idx, vtx_color, mask, whitebackground, topo):
     output, _ = dr.interpolate(vtx_color[None, ...], rast_out, mesh_t_pos_idx)
-    output = dr.antialias(output, rast_out, v_pos_clip, mesh_t_pos_idx)
+    output = dr.antialias(output, rast_out, v_pos_clip, mesh_t_pos_idx, topology_hash=topo)
     output = torch.flip(output, dims=[1])[0]
-    ones = torch.ones(mesh_v_pos.shape, dtype=torch.float, device=v_pos_clip.device)
-    color, _ = dr.interpolate(ones[None, ...], rast_out, mesh_t_pos_idx)
-    color = dr.antialias(color, rast_out, v_pos_clip, mesh_t_pos_idx)
-    mask = torch.flip(color[0, :, :], dims=[0])
     output[~mask.bool()] = 1 if whitebackground else 0
     return torch.clamp(output, 0.0, 1.0).permute(2, 0, 1)
+
+
+def render_mask(glctx, mesh_v_pos, mesh_t_pos_idx, pose, K, resolution=[800, 800]):
+    """reference :33-66 -> mask [H, W, 3]"""
+    v_pos_clip, rast_out, topo = _raster(glctx, mesh_v_pos, mesh_t_pos_idx, pose, K, resolution)
+    return _mask_from(rast_out, v_pos_clip, mesh_v_pos, mesh_t_pos_idx, topo)
+
+
+def render_mesh(glctx, mesh_v_pos, mesh_t_pos_idx, vtx_color, pose, K, resolution=[800, 800], whitebackground=False):
+    """reference :69-121 -> image [3, H, W]"""
+    v_pos_clip, rast_out, topo = _raster(glctx, mesh_v_pos, mesh_t_pos_idx, pose, K, resolution)
+    mask = _mask_from(rast_out, v_pos_clip, mesh_v_pos, mesh_t_pos_idx, topo)
+    return _image_from(rast_out, v_pos_clip, mesh_t_pos_idx, vtx_color, mask, whitebackground, topo)
 
 
 def extract_mesh(gaussians, d_xyz, d_normal, freeze_pos=False):
@@ -89,23 +110,26 @@ def mesh_renderer(glctx, gaussians, d_xyz, d_normal, fid, deform_back, appearanc
     vtx_color = appearance.step(mesh_canonical_xyz, time_input)
     if viewpoint_cam is None:
         return verts, faces, vtx_color
-    _, util = _nvdiffrast()
-    from utils.graphics_utils import fov2focal
+    dev = verts.device
     if viewpoint_cam.K is not None:
-        K = torch.tensor(viewpoint_cam.K).float().to("cuda")
+        K = torch.tensor(viewpoint_cam.K).float().to(dev)
     else:
-        focalx = fov2focal(viewpoint_cam.FoVx, viewpoint_cam.image_width)
-        focaly = fov2focal(viewpoint_cam.FoVy, viewpoint_cam.image_height)
+        import math
+        # utils/graphics_utils.fov2focal (:103-104)
+        focalx = viewpoint_cam.image_width / (2 * math.tan(viewpoint_cam.FoVx / 2))
+        focaly = viewpoint_cam.image_height / (2 * math.tan(viewpoint_cam.FoVy / 2))
         K = torch.tensor([[focalx, 0, viewpoint_cam.image_width / 2], [0, focaly, viewpoint_cam.image_height / 2],
-                          [0, 0, 1]]).float().to("cuda")
-    c2w_blender = torch.tensor(viewpoint_cam.orig_transform).cuda().float()  # blender/OpenGL camera
-    c2w_opencv = c2w_blender @ util.blender2opencv
-    pose = util.opencv2blender @ torch.inverse(c2w_opencv)
+                          [0, 0, 1]]).float().to(dev)
+    c2w_blender = torch.tensor(viewpoint_cam.orig_transform).to(dev).float()  # blender/OpenGL camera
+    b2cv = _blender2opencv(dev)
+    c2w_opencv = c2w_blender @ b2cv
+    pose = torch.inverse(b2cv) @ torch.inverse(c2w_opencv)                    # = w2c in the blender convention
     res = [viewpoint_cam.image_height, viewpoint_cam.image_width]
-    mask = render_mask(glctx, verts, faces, pose, K, resolution=res)[..., [0]]
-    mesh_image = render_mesh(glctx, verts, faces, vtx_color, pose, K, resolution=res, whitebackground=whitebackground)
-    return mask, mesh_image, verts, faces, vtx_color
-
+    # one rasterisation serves the mask and the image (reference: render_mask + render_mesh rasterise twice)
+    v_pos_clip, rast_out, topo = _raster(glctx, verts, faces, pose, K, res)
+    mask3 = _mask_from(rast_out, v_pos_clip, verts, faces, topo)
+    mesh_image = _image_from(rast_out, v_pos_clip, faces, vtx_color, mask3, whitebackground, topo)
+    return mask3[..., [0]], mesh_image, verts, faces, vtx_color
 
 def __getattr__(name):
     """Names this drop-in does not define (`mesh_shape_renderer`, `pointcloud_renderer`: PyTorch3D /

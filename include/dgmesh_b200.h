@@ -391,6 +391,36 @@ int dgloss_backward(int H, int W, const float* img, const float* gt, float lambd
                     const float* dL_dloss, float* dL_dimg, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Differentiable triangle-mesh rasterisation (next-tier row SURVEY.md 8(f)-1): the three primitives
+ * dgmesh/utils/renderer.py:33-121 (render_mask / render_mesh) takes from nvdiffrast --
+ * dr.rasterize, dr.interpolate, dr.antialias -- forward and backward, one image (batch 1).
+ * nvdiffrast is third-party and not in the reference tree: the CONTRACT of those calls is reproduced
+ * (dg-mesh_b200/csrc/meshrast.cu states it), parity is geometric.
+ *   pos[V,4]  clip-space positions (x, y, z, w), tri[F,3] int32, image H x W, row 0 = NDC y -1
+ *   rast[H,W,4] = (u, v, z/w, triangle id + 1; all zero where nothing is hit)
+ *   dgmr_rasterize      zbuf: caller scratch of 8 * H * W bytes
+ *   dgmr_rasterize_bwd  grast[H,W,4] (only .xy used) -> gpos[V,4] ACCUMULATED (caller zero-fills)
+ *   dgmr_interpolate    attr[V,C] -> out[H,W,C]
+ *   dgmr_interpolate_bwd  gout[H,W,C] -> gattr[V,C] ACCUMULATED (may be NULL), grast[H,W,4] written (may be NULL)
+ *   dgmr_antialias      color[H,W,C], opp[F,3] (vertex opposite edge k = (v_k, v_k+1) in the neighbouring
+ *                       triangle, -1 on a boundary) -> out[H,W,C]
+ *   dgmr_antialias_bwd  gout -> gcolor[H,W,C] written (may be NULL), gpos[V,4] ACCUMULATED (may be NULL)
+ * ------------------------------------------------------------------------ */
+int dgmr_rasterize(int V, int F, int W, int H, const float* pos, const int32_t* tri, void* zbuf, float* rast,
+                   void* stream);
+int dgmr_rasterize_bwd(int W, int H, const float* rast, const int32_t* tri, const float* pos, const float* grast,
+                       float* gpos, void* stream);
+int dgmr_interpolate(int W, int H, int C, const float* attr, const float* rast, const int32_t* tri, float* out,
+                     void* stream);
+int dgmr_interpolate_bwd(int W, int H, int C, const float* attr, const float* rast, const int32_t* tri,
+                         const float* gout, float* gattr, float* grast, void* stream);
+int dgmr_antialias(int W, int H, int C, const float* color, const float* rast, const float* pos,
+                   const int32_t* tri, const int32_t* opp, float* out, void* stream);
+int dgmr_antialias_bwd(int W, int H, int C, const float* color, const float* rast, const float* pos,
+                       const int32_t* tri, const int32_t* opp, const float* gout, float* gcolor, float* gpos,
+                       void* stream);
+
+/* ------------------------------------------------------------------------
  * Adaptive density control on the device (next-tier row SURVEY.md 8(f)-2): the whole of
  * GaussianModelDPSRDynamicAnchor.densify_and_prune
  * (dgmesh/scene/gaussian_model_dpsr_dynamic_anchor.py:469-551: densify_and_clone, densify_and_split

@@ -589,6 +589,35 @@ def main():
                 out["train_step"] = train_step.measure(steps=5)
             except Exception as e:  # never lose the headline line over the extra leg
                 out["train_step"] = {"error": f"{type(e).__name__}: {e}"}
+    if world > 1 and ours and not a.no_train_step:
+        # ---- BASELINE configs[3]: the FULL train step, one frame per rank (camera k on the ring,
+        # t_k = k / world), ONE all-reduce of [canonical-Gaussian grads || the five MLPs' grads] through dp.FlatGrad
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import dp
+            import train_step as ts
+            torch.cuda.empty_cache()
+            S = ts.build("ours", 200_000, 288, dev, azimuth_deg=360.0 * rank / world)   # same seed: replicated parameters
+            fg = dp.FlatGrad(S.params)
+
+            def dp_step():
+                fg.zero()
+                ts.full_step(S, t_value=rank / world, clear_grads=False)
+                fg.allreduce(average=True)
+
+            def dp_step_local():
+                fg.zero()
+                ts.full_step(S, t_value=rank / world, clear_grads=False)
+
+            ms_dp = timed(dp_step, 5, 3, world) / 5
+            ms_local = timed(dp_step_local, 5, 2, world) / 5
+            out["train_step_dp"] = {"config": "C4: full train step (200k Gaussians, grid 288), 1 frame per rank, t_k = k/N",
+                                    "ms_per_step": ms_dp, "ms_without_allreduce": ms_local,
+                                    "frames_per_s": world / (ms_dp * 1e-3), "allreduce_bytes": fg.flat.numel() * 4,
+                                    "scaling": "weak"}
+            del S, fg
+        except Exception as e:
+            out["train_step_dp"] = {"error": f"{type(e).__name__}: {e}"}
     if world > 1:
         dist.destroy_process_group()
     sys.stdout.flush()

@@ -48,9 +48,9 @@ SIGNATURES = {
     "dgp_forward": (c_int, [P, c_int, ctypes.c_double, P, P, c_int, P, P, P, c_size_t, P]),
     "dgp_backward": (c_int, [P, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
     "dgmc_workspace_size": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
-    "dgmc_count": (c_int, [c_int, P, c_float, P, c_size_t, P, P]),
-    "dgmc_emit": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
-    "dgmc_backward": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P]),
+    "dgmc_count": (c_int, [c_int, P, c_float, P, c_size_t, P, P, P, P]),
+    "dgmc_emit": (c_int, [c_int, P, c_float, P, c_size_t, P, c_int64, P, c_int64, P]),
+    "dgmc_backward": (c_int, [c_int, c_int, P, c_float, P, c_size_t, P, P, P]),
     "dgl_gemm_ws_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
     "dgl_gemm_bf16": (c_int, [c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, c_int, P, c_size_t, P]),
     "dgl_gemm_tn_bf16": (c_int, [c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, c_int, P, c_size_t, P]),
@@ -61,6 +61,9 @@ SIGNATURES = {
     "dgl_mlp_workspace": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "dgl_mlp_forward": (c_int, [P, c_int, P, P, P, c_int, P, c_size_t, P]),
     "dgl_mlp_backward": (c_int, [P, c_int, P, P, P, P, c_size_t, P, P, P]),
+    "dgl_laplacian_workspace": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
+    "dgl_laplacian_forward": (c_int, [c_int, c_int, P, P, P, P, c_size_t, P]),
+    "dgl_laplacian_backward": (c_int, [c_int, c_int, P, P, P, P, c_size_t, P]),
     "dgmr_rasterize": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "dgmr_rasterize_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P]),
     "dgmr_interpolate": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),

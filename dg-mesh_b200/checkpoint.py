@@ -124,20 +124,52 @@ def load_gaussians_ply(path, max_sh_degree=3):
     return out
 
 
+def _rng_state():
+    """Every generator the training loop draws from: python `random` (camera pick, train.py:150), numpy, the
+    torch CPU generator and all CUDA generators (torch.randn(..., device='cuda'), torch.normal in densification)."""
+    import random
+    np_state = np.random.get_state()
+    st = {"torch": torch.get_rng_state(),
+          "python": torch.tensor(list(random.getstate()[1]), dtype=torch.int64),
+          "python_version": int(random.getstate()[0]),
+          "numpy_keys": torch.from_numpy(np_state[1].astype(np.int64)),
+          "numpy_meta": torch.tensor([int(np_state[2]), int(np_state[3])], dtype=torch.int64),
+          "numpy_gauss": float(np_state[4])}
+    if torch.cuda.is_available():
+        st["cuda"] = torch.cuda.get_rng_state_all()
+    return st
+
+
+def _restore_rng(st):
+    import random
+    torch.set_rng_state(st["torch"].cpu())
+    if "python" in st:
+        random.setstate((int(st["python_version"]), tuple(int(x) for x in st["python"].tolist()), None))
+    if "numpy_keys" in st:
+        np.random.set_state(("MT19937", st["numpy_keys"].numpy().astype(np.uint32), int(st["numpy_meta"][0]),
+                             int(st["numpy_meta"][1]), float(st["numpy_gauss"])))
+    if "cuda" in st and torch.cuda.is_available() and len(st["cuda"]) == torch.cuda.device_count():
+        torch.cuda.set_rng_state_all([t.cpu() for t in st["cuda"]])
+
+
 def save_training_state(path, iteration, optimizers, extra=None):
     """optimizers: {name: torch.optim.Optimizer}; extra: {name: tensor} (e.g. xyz_gradient_accum, denom,
-    max_radii2D) -- with the PLY and the networks' .pth files this makes a resume exact."""
+    max_radii2D) -- with the PLY, the networks' .pth files and the generator states kept here (python, numpy,
+    torch CPU and CUDA) a resume is exact.  The payload is tensors / numbers / strings only, so it is read
+    back with `weights_only=True` (no arbitrary unpickling)."""
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    torch.save({"format": "dgmesh_b200.training_state.v1", "iteration": int(iteration),
+    torch.save({"format": "dgmesh_b200.training_state.v2", "iteration": int(iteration),
                 "optimizers": {k: o.state_dict() for k, o in optimizers.items()},
                 "extra": {k: v.detach().cpu() for k, v in (extra or {}).items()},
-                "rng": {"torch": torch.get_rng_state()}}, path)
+                "rng": _rng_state()}, path)
 
 
-def load_training_state(path, optimizers=None, map_location="cpu"):
-    st = torch.load(path, map_location=map_location, weights_only=False)
-    if st.get("format") != "dgmesh_b200.training_state.v1":
+def load_training_state(path, optimizers=None, map_location="cpu", restore_rng=True):
+    st = torch.load(path, map_location=map_location, weights_only=True)
+    if st.get("format") not in ("dgmesh_b200.training_state.v1", "dgmesh_b200.training_state.v2"):
         raise ValueError("not a dgmesh_b200 training state")
     for k, o in (optimizers or {}).items():
         o.load_state_dict(st["optimizers"][k])
+    if restore_rng and "rng" in st:
+        _restore_rng(st["rng"])
     return st

@@ -482,13 +482,13 @@ int dgp_backward(void* plan, int N, const float* V, const float* Nrm, int mode, 
 }
 
 int dgmc_workspace_size(int G, size_t* bytes) {
-  if (G < 2 || G > 1024 || !bytes) return bad("dgmc_workspace_size: bad argument");
+  if (G < 2 || G > 800 || !bytes) return bad("dgmc_workspace_size: bad argument (2 <= G <= 800)");
   dgm::McWS::from(nullptr, G, bytes);
   return DGM_OK;
 }
 
 static int dgmc_check(int G, const float* phi, void* ws, size_t ws_bytes) {
-  if (G < 2 || G > 1024 || !phi || !ws) return bad("marching cubes: bad argument");
+  if (G < 2 || G > 800 || !phi || !ws) return bad("marching cubes: bad argument (2 <= G <= 800)");
   size_t need;
   dgm::McWS::from(nullptr, G, &need);
   if (ws_bytes < need) {
@@ -498,26 +498,29 @@ static int dgmc_check(int G, const float* phi, void* ws, size_t ws_bytes) {
   return DGM_OK;
 }
 
-int dgmc_count(int G, const float* phi, float iso, void* ws, size_t ws_bytes, int32_t* totals, void* stream) {
+int dgmc_count(int G, const float* phi, float iso, void* ws, size_t ws_bytes, int32_t* totals, int32_t* totals_host,
+               void* totals_event, void* stream) {
   int rc = dgmc_check(G, phi, ws, ws_bytes);
   if (rc != DGM_OK) return rc;
   if (!totals) return bad("dgmc_count: null totals");
-  return check(dgm::launch_mc_count(G, phi, iso, ws, totals, (cudaStream_t)stream));
+  return check(dgm::launch_mc_count(G, phi, iso, ws, totals, totals_host, (cudaEvent_t)totals_event,
+                                    (cudaStream_t)stream));
 }
 
-int dgmc_emit(int G, const float* phi, float iso, void* ws, size_t ws_bytes, float* verts, int32_t* faces,
-              void* stream) {
+int dgmc_emit(int G, const float* phi, float iso, void* ws, size_t ws_bytes, float* verts, int64_t V_cap,
+              int32_t* faces, int64_t F_cap, void* stream) {
   int rc = dgmc_check(G, phi, ws, ws_bytes);
   if (rc != DGM_OK) return rc;
-  return check(dgm::launch_mc_emit(G, phi, iso, ws, verts, faces, (cudaStream_t)stream));
+  if (V_cap < 0 || F_cap < 0 || (V_cap > 0 && !verts) || (F_cap > 0 && !faces)) return bad("dgmc_emit: bad argument");
+  return check(dgm::launch_mc_emit(G, phi, iso, ws, verts, V_cap, faces, F_cap, (cudaStream_t)stream));
 }
 
-int dgmc_backward(int G, const float* phi, float iso, void* ws, size_t ws_bytes, const float* dL_dverts,
+int dgmc_backward(int G, int V, const float* phi, float iso, void* ws, size_t ws_bytes, const float* dL_dverts,
                   float* dL_dphi, void* stream) {
   int rc = dgmc_check(G, phi, ws, ws_bytes);
   if (rc != DGM_OK) return rc;
-  if (!dL_dphi) return bad("dgmc_backward: null output");
-  return check(dgm::launch_mc_backward(G, phi, iso, ws, dL_dverts, dL_dphi, (cudaStream_t)stream));
+  if (!dL_dphi || V < 0 || (V > 0 && !dL_dverts)) return bad("dgmc_backward: bad argument");
+  return check(dgm::launch_mc_backward(G, V, phi, iso, ws, dL_dverts, dL_dphi, (cudaStream_t)stream));
 }
 
 int dgl_gemm_ws_bytes(int M, int N, int K, size_t* bytes) {
@@ -645,6 +648,31 @@ int dgloss_backward(int H, int W, const float* img, const float* gt, float lambd
     return DGM_E_WORKSPACE;
   }
   return check(dgm::launch_loss_backward(H, W, img, gt, lambda_dssim, mode, dL_dloss, dL_dimg, ws, (cudaStream_t)stream));
+}
+
+int dgl_laplacian_workspace(int V, size_t* bytes) {
+  if (V < 0 || !bytes) return bad("dgl_laplacian_workspace: bad argument");
+  *bytes = dgm::laplacian_ws_bytes(V);
+  return DGM_OK;
+}
+int dgl_laplacian_forward(int V, int F, const float* verts, const int32_t* tri, float* out, void* ws,
+                          size_t ws_bytes, void* stream) {
+  if (V < 0 || F < 0 || !out || !ws || (V > 0 && !verts) || (F > 0 && !tri)) return bad("dgl_laplacian_forward: bad argument");
+  if (ws_bytes < dgm::laplacian_ws_bytes(V)) {
+    strncpy(g_last_error, "dgl_laplacian_forward: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  return check(dgm::launch_laplacian_forward(V, F, verts, tri, out, ws, (cudaStream_t)stream));
+}
+int dgl_laplacian_backward(int V, int F, const int32_t* tri, const float* dL_dloss, float* dverts, void* ws,
+                           size_t ws_bytes, void* stream) {
+  if (V < 0 || F < 0 || !ws || (V > 0 && !dverts) || (F > 0 && !tri)) return bad("dgl_laplacian_backward: bad argument");
+  if (ws_bytes < dgm::laplacian_ws_bytes(V)) {
+    strncpy(g_last_error, "dgl_laplacian_backward: workspace too small", sizeof(g_last_error) - 1);
+    return DGM_E_WORKSPACE;
+  }
+  if (V == 0) return DGM_OK;
+  return check(dgm::launch_laplacian_backward(V, F, tri, dL_dloss, dverts, ws, (cudaStream_t)stream));
 }
 
 int dgmr_rasterize(int V, int F, int W, int H, const float* pos, const int32_t* tri, void* zbuf, float* rast,

@@ -9,4 +9,9 @@ cudaError_t launch_loss_forward(int H, int W, const float* img, const float* gt,
                                 void* ws, cudaStream_t s);
 cudaError_t launch_loss_backward(int H, int W, const float* img, const float* gt, float lam, int mode,
                                  const float* upstream, float* dL_dimg, void* ws, cudaStream_t s);
+size_t laplacian_ws_bytes(int V);
+cudaError_t launch_laplacian_forward(int V, int F, const float* verts, const int* tri, float* out, void* ws,
+                                     cudaStream_t s);
+cudaError_t launch_laplacian_backward(int V, int F, const int* tri, const float* dL_dloss, float* dverts, void* ws,
+                                      cudaStream_t s);
 }  // namespace dgm

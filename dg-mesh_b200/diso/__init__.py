@@ -18,6 +18,21 @@ if _root not in sys.path:
 import _dgm_lib  # noqa: E402
 
 
+_caps = {}      # (device, G) -> [V capacity, F capacity] of the previous surfaces (+ head-room)
+_notify = {}    # device -> (handle, event, host pointer, ctypes view): early notification of {V, F}
+
+
+def _notifier(dev_index):
+    n = _notify.get(dev_index)
+    if n is None:
+        lib = _dgm_lib.lib()
+        h = _dgm_lib.c_void_p()
+        _dgm_lib.check(lib.dgm_notify_create(_dgm_lib.byref(h)), "dgm_notify_create")
+        host = lib.dgm_notify_host(h)
+        n = _notify[dev_index] = (h, lib.dgm_notify_event(h), host, (_dgm_lib.c_int32 * 2).from_address(host))
+    return n
+
+
 class _MCFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, grid, isovalue, normalize):
@@ -27,24 +42,43 @@ class _MCFunction(torch.autograd.Function):
             raise ValueError("DiffMC: CUDA tensor required (no CPU fallback)")
         lib = _dgm_lib.lib()
         g = grid.contiguous().float()
-        G = g.shape[0]
+        G, dev = g.shape[0], g.device
         nbytes = _dgm_lib.c_size_t()
         _dgm_lib.check(lib.dgmc_workspace_size(G, nbytes), "dgmc_workspace_size")
-        ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=g.device)
-        totals = torch.empty((2,), dtype=torch.int32, device=g.device)
+        ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)
+        totals = torch.empty((2,), dtype=torch.int32, device=dev)
         st = _dgm_lib.stream_ptr()
+        handle, event, host_ptr, words = _notifier(dev.index)
         _dgm_lib.check(lib.dgmc_count(G, g.data_ptr(), float(isovalue), ws.data_ptr(), nbytes.value,
-                                      totals.data_ptr(), st), "dgmc_count")
-        V, F = (int(x) for x in totals.cpu())  # the one host sync: output sizes are data dependent
-        verts = torch.empty((V, 3), dtype=torch.float32, device=g.device)
-        faces = torch.empty((F, 3), dtype=torch.int32, device=g.device)
-        if V:
+                                      totals.data_ptr(), host_ptr, event, st), "dgmc_count")
+        # Output sizes are data dependent (the reference's diso sizes its outputs with a host read too).  The
+        # emission is enqueued OPTIMISTICALLY with the capacities the previous surface needed, THEN the host
+        # waits for {V, F} (mirrored into pinned memory behind the count pass): the GPU keeps working while
+        # the host waits, and only a surface that outgrew the capacity is emitted a second time.
+        key = (dev.index, G)
+        cap = _caps.get(key)
+
+        def emit(vc, fc):
+            v = torch.empty((vc, 3), dtype=torch.float32, device=dev)
+            f = torch.empty((fc, 3), dtype=torch.int32, device=dev)
             _dgm_lib.check(lib.dgmc_emit(G, g.data_ptr(), float(isovalue), ws.data_ptr(), nbytes.value,
-                                         verts.data_ptr(), faces.data_ptr(), st), "dgmc_emit")
+                                         _dgm_lib.ptr(v), vc, _dgm_lib.ptr(f), fc, st), "dgmc_emit")
+            return v, f
+
+        out = emit(*cap) if cap else None
+        _dgm_lib.check(lib.dgm_notify_wait(handle), "dgm_notify_wait")
+        V, F = int(words[0]), int(words[1])
+        if out is None or V > cap[0] or F > cap[1]:
+            out = emit(V, F) if (V or F) else (torch.empty((0, 3), dtype=torch.float32, device=dev),
+                                               torch.empty((0, 3), dtype=torch.int32, device=dev))
+        if len(_caps) > 32:
+            _caps.clear()
+        _caps[key] = [max(cap[0] if cap else 0, int(V * 1.25) + 1024), max(cap[1] if cap else 0, int(F * 1.25) + 1024)]
+        verts, faces = out[0][:V], out[1][:F]
         if not normalize:
             verts = verts * float(G - 1)
         ctx.save_for_backward(g, ws)
-        ctx.iso, ctx.normalize, ctx.nbytes = float(isovalue), normalize, nbytes.value
+        ctx.iso, ctx.normalize, ctx.nbytes, ctx.V = float(isovalue), normalize, nbytes.value, V
         ctx.mark_non_differentiable(faces)
         return verts, faces
 
@@ -56,10 +90,8 @@ class _MCFunction(torch.autograd.Function):
         dv = dverts.contiguous().float()
         if not ctx.normalize:
             dv = dv * float(G - 1)
-        if dv.shape[0] == 0:
-            return torch.zeros_like(g), None, None
-        _dgm_lib.check(_dgm_lib.lib().dgmc_backward(G, g.data_ptr(), ctx.iso, ws.data_ptr(), ctx.nbytes,
-                                                    dv.data_ptr(), dphi.data_ptr(), _dgm_lib.stream_ptr()),
+        _dgm_lib.check(_dgm_lib.lib().dgmc_backward(G, ctx.V, g.data_ptr(), ctx.iso, ws.data_ptr(), ctx.nbytes,
+                                                    _dgm_lib.ptr(dv), dphi.data_ptr(), _dgm_lib.stream_ptr()),
                        "dgmc_backward")
         return dphi, None, None
 

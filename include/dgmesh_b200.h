@@ -250,17 +250,21 @@ int dgp_backward(void* plan, int N, const float* V, const float* Nrm, int mode,
  * dgmesh/scene/gaussian_model_dpsr_dynamic_anchor.py:704,851 (third-party package, not in the
  * reference tree: only the CONTRACT at the call sites is reproduced).
  *   phi[G,G,G] fp32, iso  ->  verts[V,3] fp32 in [0,1]^3 (index/(G-1)), faces[F,3] int32
- * Two-phase because V and F are data dependent: dgmc_count writes totals[2] = {V, F}
- * (device int32); the caller reads them (the one host sync, as in the reference where diso
- * returns exactly-sized tensors), allocates, and calls dgmc_emit with the same workspace.
- * dgmc_backward: dL_dverts[V,3] -> dL_dphi[G,G,G] (fully written).
+ * V and F are data dependent.  dgmc_count sweeps the grid once and writes totals[2] = {V, F} to a device
+ * int32 pair and, when given, to a pinned device-mapped host pair (`totals_host`, e.g. dgm_notify_host) with
+ * `totals_event` (a cudaEvent_t) recorded behind it; dgmc_emit writes up to V_cap vertices and F_cap faces
+ * (bounds enforced on the device), so a caller may enqueue it OPTIMISTICALLY with the capacities of the previous
+ * call before it knows V and F, wait for the event, and re-run dgmc_emit only if something did not fit -- the
+ * drop-in Python layer does that; the reference's diso synchronises to size its outputs as well.
+ * G <= 800 (face references are packed into int32).
+ * dgmc_backward: dL_dverts[V,3] -> dL_dphi[G,G,G] (fully written); V as returned by dgmc_count.
  * ------------------------------------------------------------------------ */
 int dgmc_workspace_size(int G, size_t* bytes);
 int dgmc_count(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
-               int32_t* totals, void* stream);
+               int32_t* totals, int32_t* totals_host, void* totals_event, void* stream);
 int dgmc_emit(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
-              float* verts, int32_t* faces, void* stream);
-int dgmc_backward(int G, const float* phi, float iso, void* ws, size_t ws_bytes,
+              float* verts, int64_t V_cap, int32_t* faces, int64_t F_cap, void* stream);
+int dgmc_backward(int G, int V, const float* phi, float iso, void* ws, size_t ws_bytes,
                   const float* dL_dverts, float* dL_dphi, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -389,6 +393,17 @@ int dgloss_forward(int H, int W, const float* img, const float* gt, float lambda
                    float* out3, void* ws, size_t ws_bytes, void* stream);
 int dgloss_backward(int H, int W, const float* img, const float* gt, float lambda_dssim, int mode,
                     const float* dL_dloss, float* dL_dimg, void* ws, size_t ws_bytes, void* stream);
+
+/* Laplacian mesh regulariser (umbrella operator) of the mesh branch:
+ * nvdiffrast_utils.regularizer.laplace_regularizer_const(verts, faces)
+ * (dgmesh/nvdiffrast_utils/regularizer.py:40-59, used at dgmesh/train.py:277-283).
+ *   verts[V,3], tri[F,3] int32 -> out[1] = mean((T / max(n, 1))^2); the workspace carries the
+ *   per-vertex state to dgl_laplacian_backward: dL_dloss[1] (NULL = 1) -> dverts[V,3] (fully written). */
+int dgl_laplacian_workspace(int V, size_t* bytes);
+int dgl_laplacian_forward(int V, int F, const float* verts, const int32_t* tri, float* out, void* ws,
+                          size_t ws_bytes, void* stream);
+int dgl_laplacian_backward(int V, int F, const int32_t* tri, const float* dL_dloss, float* dverts, void* ws,
+                           size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Differentiable triangle-mesh rasterisation (next-tier row SURVEY.md 8(f)-1): the three primitives

@@ -88,3 +88,25 @@ def test_training_state_resume_is_exact(tmp_path):
         (w2 ** 2).sum().backward()
         opt2.step()
         assert torch.equal(w2.detach(), ref[k])
+
+
+def test_training_state_restores_every_generator_and_loads_without_pickle(tmp_path):
+    """ADVICE r1: the loop draws from python `random`, numpy and torch (CPU + CUDA): all are saved and restored;
+    the file loads with weights_only=True."""
+    import random
+    import numpy as np
+    import checkpoint
+    p = torch.nn.Parameter(torch.randn(4, 3))
+    opt = torch.optim.Adam([p], lr=0.1)
+    p.grad = torch.ones_like(p)
+    opt.step()
+    random.seed(3), np.random.seed(4), torch.manual_seed(5)
+    path = str(tmp_path / "state.pt")
+    checkpoint.save_training_state(path, 7, {"g": opt}, {"denom": torch.arange(5.0)})
+    want = (random.random(), float(np.random.rand()), float(torch.rand(1)))
+    random.seed(0), np.random.seed(0), torch.manual_seed(0)
+    opt2 = torch.optim.Adam([p], lr=0.1)
+    st = checkpoint.load_training_state(path, {"g": opt2})
+    assert st["iteration"] == 7 and torch.equal(st["extra"]["denom"], torch.arange(5.0))
+    assert (random.random(), float(np.random.rand()), float(torch.rand(1))) == want
+    assert torch.equal(opt2.state_dict()["state"][0]["exp_avg"], opt.state_dict()["state"][0]["exp_avg"])

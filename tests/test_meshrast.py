@@ -138,7 +138,9 @@ def test_sphere_mask_area_translation_invariance_and_finite_differences():
     f = 1.0 / math.tan(0.6911 / 2)
     r_pix = f * math.tan(math.asin(1 / 4.0)) * H / 2
     m = mask_of(torch.zeros(3, device="cuda"))
-    assert abs(float(m.sum()) / (math.pi * r_pix ** 2) - 1) < 5e-3
+    # the icosphere is INSCRIBED in the sphere: its silhouette is a polygon slightly inside the disc
+    # (edge angle ~0.16 rad at 3 subdivisions -> ~0.5 % less area), never outside it
+    assert -1.2e-2 < float(m.sum()) / (math.pi * r_pix ** 2) - 1 < 1e-3
     assert float(m.max()) <= 1.0 + 1e-6 and float(m.min()) >= 0.0
     # sub-pixel translations parallel to the image plane keep the covered area (antialiased, not aliased)
     sums = [float(mask_of(torch.tensor([dx, 0.0, 0.0], device="cuda")).sum()) for dx in (0.0, 0.004, 0.009, 0.013)]
@@ -179,7 +181,7 @@ def test_renderer_mask_and_mesh_image_through_the_reference_call_sequence():
     assert mask.shape == (H, W, 3) and img.shape == (3, H, W)
     assert 0.0 <= float(mask.min()) and float(mask.max()) <= 1.0 + 1e-6
     r_pix = focal * math.tan(math.asin(0.8 / 4.0))
-    assert abs(float(mask[..., 0].sum()) / (math.pi * r_pix ** 2) - 1) < 5e-3
+    assert -5e-3 < float(mask[..., 0].sum()) / (math.pi * r_pix ** 2) - 1 < 1e-3      # inscribed polyhedron (5 subdivisions)
     assert torch.all(img[:, 0, 0] == 1.0) and float(img[:, H // 2, W // 2].min()) >= 0.0
     gt = torch.zeros(H, W, 1, device="cuda")
     ((mask[..., :1] - gt).abs().mean() * 100 + (img - 0.5).abs().mean()).backward()

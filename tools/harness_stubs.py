@@ -120,6 +120,57 @@ def _make_nvdiffrast():
     return pkg, t
 
 
+def _make_trimesh():
+    """The handful of trimesh features the DPSR-phase initialisation and the anchoring use
+    (gaussian_model_dpsr_dynamic_anchor.py:705-716, 745-750): Trimesh(vertices, faces) with face_normals /
+    triangles_center / export, and trimesh.sample.sample_surface (area-weighted, numpy generator)."""
+    m = types.ModuleType("trimesh")
+
+    class Trimesh:
+        def __init__(self, vertices=None, faces=None, **kw):
+            self.vertices = np.asarray(vertices, dtype=np.float64).reshape(-1, 3)
+            self.faces = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+
+        @property
+        def triangles(self):
+            return self.vertices[self.faces]
+
+        @property
+        def triangles_center(self):
+            return self.triangles.mean(1)
+
+        def _cross(self):
+            t = self.triangles
+            return np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])
+
+        @property
+        def area_faces(self):
+            return 0.5 * np.linalg.norm(self._cross(), axis=1)
+
+        @property
+        def face_normals(self):
+            c = self._cross()
+            return c / np.maximum(np.linalg.norm(c, axis=1, keepdims=True), 1e-20)
+
+        def export(self, path=None, *a, **k):
+            return None
+
+    def sample_surface(mesh, count, **kw):
+        area = mesh.area_faces
+        p = area / area.sum()
+        idx = np.random.choice(len(area), size=int(count), p=p)
+        t = mesh.triangles[idx]
+        r1, r2 = np.sqrt(np.random.random(int(count)))[:, None], np.random.random(int(count))[:, None]
+        pts = (1 - r1) * t[:, 0] + r1 * (1 - r2) * t[:, 1] + r1 * r2 * t[:, 2]
+        return pts, idx
+
+    sample = types.ModuleType("trimesh.sample")
+    sample.sample_surface = sample_surface
+    m.Trimesh, m.sample = Trimesh, sample
+    m.load = mock.MagicMock()
+    return m, sample
+
+
 def _make_pytorch3d():
     import torch
     pkg = mock.MagicMock()
@@ -172,6 +223,8 @@ def install():
         sys.modules["plyfile"] = _make_plyfile()
     if absent("imageio"):
         sys.modules["imageio"] = _make_imageio()
+    if absent("trimesh"):
+        sys.modules["trimesh"], sys.modules["trimesh.sample"] = _make_trimesh()
     if absent("nvdiffrast"):
         pkg, t = _make_nvdiffrast()
         sys.modules["nvdiffrast"], sys.modules["nvdiffrast.torch"] = pkg, t
@@ -180,7 +233,7 @@ def install():
         sys.modules["pytorch3d"], sys.modules["pytorch3d.ops"] = pkg, ops
         for sub in ("structures", "renderer", "loss", "io"):
             sys.modules[f"pytorch3d.{sub}"] = mock.MagicMock()
-    for name in ("diso", "trimesh", "open3d", "pytorch_msssim", "torchgeometry", "kiui", "lpips", "skimage",
+    for name in ("diso", "open3d", "pytorch_msssim", "torchgeometry", "kiui", "lpips", "skimage",
                  "skimage.measure", "igl", "wis3d", "emd", "glfw", "external", "sklearn", "sklearn.neighbors",
                  "matplotlib", "matplotlib.pyplot", "mmcv", "tensorboard"):
         if absent(name):

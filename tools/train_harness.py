@@ -208,11 +208,13 @@ def compare(fa, fb, tol):
     a, b = (json.loads(open(f).read().strip().splitlines()[-1]) for f in (fa, fb))
     n = min(len(a["loss"]), len(b["loss"]))
     worst = max(abs(x - y) / max(abs(y), 1e-6) for x, y in zip(a["loss"][:n], b["loss"][:n])) if n else None
+    ng = max((abs(x - y) / max(y, 1) for x, y in zip(a["n_gauss"][:n], b["n_gauss"][:n])), default=None)
     res = {"iterations_compared": n, "max_rel_loss_diff": worst,
-           "n_gauss_equal": a["n_gauss"][:n] == b["n_gauss"][:n],
+           "max_rel_gaussian_count_diff": ng, "gaussian_counts_last": [a["n_gauss"][n - 1], b["n_gauss"][n - 1]] if n else None,
            "errors": [a.get("error"), b.get("error")],
            "ms_per_iter": {a["stack"]: a["iter_ms_median_last_half"], b["stack"]: b["iter_ms_median_last_half"]}}
-    res["ok"] = bool(n and worst is not None and worst < tol and not a.get("error") and not b.get("error"))
+    res["ok"] = bool(n and worst is not None and worst < tol and ng is not None and ng < 0.02 and
+                     not a.get("error") and not b.get("error"))
     print(json.dumps(res))
     return 0 if res["ok"] else 1
 

@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Full training-step time (deformation MLPs + rasterizer + DPSR + marching
-cubes + vertex MLPs, forward and backward) for this implementation and, beside it, for the reference's
-own modules on the same GPU: fp32 PyTorch MLPs and DPSR (oracle/_ref/refpy), the stock CUDA rasterizer
-(oracle/_ref).  `diso` (DiffMC) does not exist in the reference tree, so BOTH arms use this repo's
-marching cubes; the mesh image loss needs nvdiffrast and is replaced by verts.sum() + colour.sum() so
-the DPSR / MC / vertex-MLP backward still runs.
+"""Full training-step time (the steady-state iteration of dgmesh/train.py:150-311
+past dpsr_iter: 4 N-sized deformation MLPs, Gaussian rasterizer, image loss (L1 + SSIM), DPSR, marching cubes,
+2 V-sized vertex MLPs, mesh rasterisation (mask + image), mask / mesh-image / Laplacian losses; forward and
+backward) for this implementation and, beside it, for the reference's own modules on the same GPU: fp32
+PyTorch MLPs, DPSR and loss functions (oracle/_ref/refpy), the stock CUDA rasterizer (oracle/_ref), the
+reference's Laplacian arithmetic.  Two third-party packages of the reference are not in its tree and not
+installable here -- `diso` (marching cubes) and `nvdiffrast` (mesh rasteriser) -- so BOTH arms use this repo's
+kernels for those two stages (which favours the reference arm: its own would be no faster).
 
     python tools/train_step.py [--gaussians 200000] [--grid 288] [--steps 10]
 prints one JSON object with the step time and a per-component breakdown of both arms.
@@ -24,7 +26,7 @@ for p in (ROOT, os.path.join(ROOT, "dg-mesh_b200"), os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 
-def build(arm, n, G, dev):
+def build(arm, n, G, dev, azimuth_deg=30.0):
     import synth
     import util
     torch.manual_seed(0)
@@ -39,7 +41,16 @@ def build(arm, n, G, dev):
             return None
         tu, DPSR = ref.time_utils, ref.dpsr.DPSR
     from diso import DiffMC
-    renderer = importlib.import_module("utils.renderer")
+    renderer = importlib.import_module("utils.renderer")       # this repo's mesh branch glue in both arms
+    if arm == "ours":
+        loss_utils = importlib.import_module("utils.loss_utils")
+        laplacian = importlib.import_module("nvdiffrast_utils.regularizer").laplace_regularizer_const
+    else:
+        import importlib.util as ilu
+        spec = ilu.spec_from_file_location("refpy.loss_utils", os.path.join(util.REF_DIR, "refpy", "loss_utils.py"))
+        loss_utils = ilu.module_from_spec(spec)
+        spec.loader.exec_module(loss_utils)
+        laplacian = None
     sc = synth.gaussian_scene(n=n, seed=0, device=dev)
     g = torch.Generator().manual_seed(3)
     d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1)
@@ -59,13 +70,19 @@ def build(arm, n, G, dev):
         dpsr = dpsr.to(dev)
     gauss = SimpleNamespace(gaussian_center=torch.zeros(3, device=dev), gaussian_scale=torch.tensor([1.2 * 1.3], device=dev),
                             dpsr=dpsr, diffmc=DiffMC(dtype=torch.float32).to(dev))
-    cam = synth.look_at_camera(azimuth_deg=30.0, elevation_deg=20.0, radius=4.0, width=800, height=800, device=dev)
+    cam = synth.look_at_camera(azimuth_deg=azimuth_deg, elevation_deg=20.0, radius=4.0, width=800, height=800,
+                               device=dev)
     bg = torch.ones(3, device=dev)
     gt = torch.rand(3, 800, 800, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    gt_mask = (torch.rand(800, 800, 1, device=dev, generator=torch.Generator(device=dev).manual_seed(6)) > 0.5).float()
+    # what scene/cameras.py keeps for the mesh rasteriser: the blender camera-to-world matrix
+    w2c = cam.world_view_transform.t()
+    cam.orig_transform = (torch.inverse(w2c) @ torch.diag(torch.tensor([1.0, -1.0, -1.0, 1.0], device=dev))).cpu().numpy()
+    cam.K = None
     params = [P.xyz, P.normal, P.opacities, P.scales, P.rotations, P.shs, P.thres] + \
         [q for m in vars(nets).values() for q in m.parameters()]
     return SimpleNamespace(arm=arm, dgr=dgr, renderer=renderer, P=P, nets=nets, gauss=gauss, cam=cam, bg=bg, gt=gt,
-                           params=params, n=n, synth=synth)
+                           gt_mask=gt_mask, loss_utils=loss_utils, laplacian=laplacian, params=params, n=n, synth=synth)
 
 
 def mlp_part(S, t):
@@ -88,23 +105,56 @@ def raster_part(S, d_xyz, d_rot, d_scale):
     m2d = torch.zeros_like(P.xyz, requires_grad=True)
     img, radii = S.dgr.GaussianRasterizer(rs)(means3D=P.xyz + d_xyz, means2D=m2d, opacities=P.opacities, shs=P.shs,
                                               scales=P.scales + d_scale, rotations=P.rotations + d_rot)
-    return (img - S.gt).abs().mean()
+    return _img_loss(S, img, S.gt)
+
+
+LAMBDA_DSSIM = 0.2
+
+
+def _img_loss(S, img, gt):
+    """(1 - l) L1 + l (1 - SSIM), dgmesh/train.py:308-311"""
+    if S.arm == "ours":
+        return S.loss_utils.image_loss(img, gt, LAMBDA_DSSIM)
+    lu = S.loss_utils
+    return (1.0 - LAMBDA_DSSIM) * lu.l1_loss(img, gt) + LAMBDA_DSSIM * (1.0 - lu.ssim(img, gt))
+
+
+def _laplacian_ref(v_pos, t_pos_idx):
+    """nvdiffrast_utils/regularizer.py:40-59, the reference's arithmetic (its module cannot be imported without
+    nvdiffrast)"""
+    term = torch.zeros_like(v_pos)
+    norm = torch.zeros_like(v_pos[..., 0:1])
+    v0, v1, v2 = v_pos[t_pos_idx[:, 0], :], v_pos[t_pos_idx[:, 1], :], v_pos[t_pos_idx[:, 2], :]
+    term.scatter_add_(0, t_pos_idx[:, 0:1].repeat(1, 3), (v1 - v0) + (v2 - v0))
+    term.scatter_add_(0, t_pos_idx[:, 1:2].repeat(1, 3), (v0 - v1) + (v2 - v1))
+    term.scatter_add_(0, t_pos_idx[:, 2:3].repeat(1, 3), (v0 - v2) + (v1 - v2))
+    two = torch.ones_like(v0) * 2.0
+    norm.scatter_add_(0, t_pos_idx[:, 0:1], two)
+    norm.scatter_add_(0, t_pos_idx[:, 1:2], two)
+    norm.scatter_add_(0, t_pos_idx[:, 2:3], two)
+    term = term / torch.clamp(norm, min=1.0)
+    return torch.mean(term ** 2)
 
 
 def mesh_part(S, d_xyz, d_normal, t1):
+    """train.py:238-283: mesh_renderer -> mask loss, mesh image loss, Laplacian"""
     g = S.gauss
     g.get_xyz, g.get_normal, g.density_thres_param = S.P.xyz, S.P.normal, S.P.thres
-    verts, faces = S.renderer.extract_mesh(g, d_xyz, d_normal)
-    tv = t1.expand(verts.shape[0], 1)
-    back, _, _, _ = S.nets.deform_back(verts.detach(), tv)
-    color = S.nets.appearance(verts + back, tv)
-    return verts.sum() * 1e-3 + color.mean(), verts.shape[0]
+    back = SimpleNamespace(step=lambda x, t: S.nets.deform_back(x, t))
+    app = SimpleNamespace(step=lambda x, t: S.nets.appearance(x, t))
+    mask, mesh_image, verts, faces, _ = S.renderer.mesh_renderer(None, g, d_xyz, d_normal, t1[0], back, app, False,
+                                                                 True, S.cam)
+    mask_loss = (mask - S.gt_mask).abs().mean() * 100
+    mesh_img_loss = _img_loss(S, mesh_image, S.gt)
+    lap = (S.laplacian(verts, faces.long()) if S.arm == "ours" else _laplacian_ref(verts, faces.long())) * 1000 * 0.5
+    return mask_loss + mesh_img_loss + lap, verts.shape[0]
 
 
-def full_step(S):
-    for q in S.params:
-        q.grad = None
-    t1 = torch.full((1, 1), 0.37, device=S.bg.device)
+def full_step(S, t_value=0.37, clear_grads=True):
+    if clear_grads:
+        for q in S.params:
+            q.grad = None
+    t1 = torch.full((1, 1), float(t_value), device=S.bg.device)
     t = t1.expand(S.n, 1)
     d_xyz, d_rot, d_scale, d_normal, cycle = mlp_part(S, t)
     loss = raster_part(S, d_xyz, d_rot, d_scale) + cycle
@@ -143,15 +193,17 @@ def components(S, steps):
         z = torch.zeros_like(S.P.xyz)
         mesh_part(S, z, z, t1)[0].backward()
 
-    return {"mlp_4xN_ms": timeit(f_mlp, steps), "raster_ms": timeit(f_raster, steps),
-            "dpsr_mc_2xV_mlp_ms": timeit(f_mesh, steps)}
+    return {"mlp_4xN_ms": timeit(f_mlp, steps), "raster_and_image_loss_ms": timeit(f_raster, steps),
+            "mesh_branch_ms": timeit(f_mesh, steps)}
 
 
 def measure(n=200_000, G=288, steps=10, arms=("ours", "reference")):
     dev = torch.device("cuda")
-    out = {"config": f"C3: {n} Gaussians, 800x800, grid {G}, 4 N-MLPs + raster + DPSR + MC + 2 V-MLPs, fwd+bwd",
-           "note": "marching cubes is this repo's kernel in both arms (diso is absent from the reference tree); "
-                   "reference MLPs/DPSR are its fp32 PyTorch modules, reference rasterizer its stock CUDA build"}
+    out = {"config": f"C3: {n} Gaussians, 800x800, grid {G}: 4 N-MLPs + Gaussian raster + L1/SSIM + DPSR + MC + "
+                     "2 V-MLPs + mesh raster (mask, image) + mask/L1/SSIM/Laplacian losses, fwd+bwd",
+           "note": "marching cubes and the mesh rasteriser are this repo's kernels in BOTH arms (diso / nvdiffrast are "
+                   "third-party, absent from the reference tree); the reference arm's MLPs, DPSR and losses are its fp32 "
+                   "PyTorch modules, its Gaussian rasterizer the stock CUDA build"}
     for arm in arms:
         S = build(arm, n, G, dev)
         if S is None:

@@ -196,7 +196,7 @@ class HostFeed:
         """d(L2 loss)/d(color) for the whole batch (i is None) or frame slot i."""
         torch.cuda.current_stream().wait_event(self.ev_gt)
         gt = self.d_gt if i is None else self.d_gt[i]
-        return torch.sub(color.detach(), gt.to(torch.float32).mul_(1.0 / 255.0))
+        return torch.add(color.detach(), gt, alpha=-1.0 / 255.0)   # one kernel: uint8 -> float, scale, subtract
 
     def finish(self, result):
         self.consumed.record()

@@ -218,39 +218,6 @@ __global__ void __launch_bounds__(256) sigmoid_kernel(int n, float* __restrict__
   if (i < n) y[i] = 1.f / (1.f + expf(-y[i]));
 }
 
-// column sums of a blocked bf16 activation with F features (F/8 kbs) -> db[F] (fp32 atomics).
-// One CTA per row tile; a thread owns one kb and every (256 / kbs)-th row (16-byte loads).
-__global__ void __launch_bounds__(256) colsum_blk_kernel(int F, const __nv_bfloat16* __restrict__ Z,
-                                                         float* __restrict__ db) {
-  __shared__ float s_sum[256];
-  const int kbs = F >> 3, lanes = 256 / kbs;
-  const int kb = threadIdx.x / lanes, rl = threadIdx.x % lanes;
-  s_sum[threadIdx.x] = 0.f;
-  __syncthreads();
-  const __nv_bfloat16* tile = Z + (size_t)blockIdx.x * F * ACT_R + (size_t)kb * KB_ELEMS;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = rl; r < ACT_R; r += lanes) {
-    const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)r * 8);
-    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 f = __bfloat1622float2(p2[q]);
-      acc[2 * q] += f.x;
-      acc[2 * q + 1] += f.y;
-    }
-  }
-  // lanes of one kb are contiguous (8, 64 or 128 threads): reduce inside the warp first
-  const int span = min(lanes, 32);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float a = acc[q];
-    for (int o = 1; o < span; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if ((threadIdx.x & (span - 1)) == 0) atomicAdd(&s_sum[kb * 8 + q], a);
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < F) atomicAdd(&db[threadIdx.x], s_sum[threadIdx.x]);
-}
-
 // dE[:, 64:96] (fp32 row-major) -> dZt1 blocked [Pp, 32] (features >= n_t are zero)
 __global__ void __launch_bounds__(256) tfeat_grad_kernel(int Pp, int n_t, const float* __restrict__ dE,
                                                          __nv_bfloat16* __restrict__ dZ) {
@@ -341,10 +308,11 @@ cudaError_t launch_mlp_forward(const DglNet& n, int P, const float* x, const flo
 
 // weight gradient C[256 (X features), N (Y features)] (+)= X^T Y, or its transpose
 static cudaError_t dw(const BlkView& X, const BlkView& Y, int N, int tiles, float* C, int ld, int transpose,
-                      cudaStream_t s) {
+                      cudaStream_t s, float* colsum_x = nullptr, float* colsum_y = nullptr) {
   DwArgs g = {};
   g.X = X; g.Y = Y; g.N = N; g.tiles = tiles; g.C = C; g.ld = ld; g.transpose = transpose;
   g.m_valid = WID; g.n_valid = N;
+  g.colsum_x = colsum_x; g.colsum_y = colsum_y;  // bias gradients ride along (no separate column-sum pass)
   return launch_dw_gemm(g, s);
 }
 
@@ -378,8 +346,7 @@ cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const fl
   // heads: dWh[16,256] = dZh^T . H7 (computed transposed: X = H7), dbh, dZ7 = (dZh . Wh) * relu'(H7)
   const BlkView vZh{b.dZh, (size_t)16 * ACT_R, 0};
   head_grad_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(P, Pp, n.n_out, n.sigmoid_out, g_out, out, b.dZh);
-  CK(dw(b.h(7), vZh, 16, tiles, gr.dWh, WID, 1, s));
-  colsum_blk_kernel<<<tiles, 256, 0, s>>>(16, b.dZh, gr.dbh);
+  CK(dw(b.h(7), vZh, 16, tiles, gr.dWh, WID, 1, s, nullptr, gr.dbh));
   int cur = 0;
   {
     LayerArgs g = layer(vZh, 16, (CB)n.WhT, WID, tiles);
@@ -391,12 +358,11 @@ cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const fl
     // dZ[cur] = dL/d(pre-activation of layer l)
     const BlkView vZ{b.dZ[cur], HS, 0};
     if (l == 0 || l == 5) {
-      CK(dw(vZ, b.a5(), K0, tiles, gr.dW[l], (l == 0) ? K0 : K5, 0, s));            // columns of [x_emb, t]
+      CK(dw(vZ, b.a5(), K0, tiles, gr.dW[l], (l == 0) ? K0 : K5, 0, s, gr.db[l]));  // columns of [x_emb, t]; db[l]
       if (l == 5) CK(dw(vZ, b.h(4), WID, tiles, gr.dW[l] + K0, K5, 0, s));          // columns of h4
     } else {
-      CK(dw(vZ, b.h(l - 1), WID, tiles, gr.dW[l], WID, 0, s));
+      CK(dw(vZ, b.h(l - 1), WID, tiles, gr.dW[l], WID, 0, s, gr.db[l]));
     }
-    colsum_blk_kernel<<<tiles, 256, 0, s>>>(WID, b.dZ[cur], gr.db[l]);
     if (l == 0 || l == 5) {  // gradient w.r.t. the embedded inputs (no ReLU in front of them)
       const CB We = (l == 0) ? (CB)n.WT[0] : (CB)n.WT[5] + (size_t)WID * WID;  // [256/8][96][8]
       LayerArgs g = layer(vZ, WID, We, K0, tiles);
@@ -414,14 +380,13 @@ cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const fl
   if (n.has_timenet) {
     const BlkView vT1{b.T1, HS, 0}, vZt1{b.dZt1, (size_t)32 * ACT_R, 0};
     tfeat_grad_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(Pp, n.in_t, b.dE, b.dZt1);
-    CK(dw(vT1, vZt1, 32, tiles, gr.dWt1, WID, 1, s));   // dWt1[32,256] = dZt1^T . T1 (transposed form)
-    colsum_blk_kernel<<<tiles, 256, 0, s>>>(32, b.dZt1, gr.dbt1);
+    CK(dw(vT1, vZt1, 32, tiles, gr.dWt1, WID, 1, s, nullptr, gr.dbt1));  // dWt1[32,256] = dZt1^T . T1 (transposed form)
     LayerArgs g = layer(vZt1, 32, (CB)n.Wt1T, WID, tiles);
     g.mask_bits = b.Mt1;
     g.out = b.dZ[cur ^ 1]; g.out_tile_stride = HS;
     CK(launch_layer_gemm(g, s));
-    CK(dw(BlkView{b.dZ[cur ^ 1], HS, 0}, BlkView{b.T0, (size_t)16 * ACT_R, 0}, 16, tiles, gr.dWt0, 16, 0, s));
-    colsum_blk_kernel<<<tiles, 256, 0, s>>>(WID, b.dZ[cur ^ 1], gr.dbt0);
+    CK(dw(BlkView{b.dZ[cur ^ 1], HS, 0}, BlkView{b.T0, (size_t)16 * ACT_R, 0}, 16, tiles, gr.dWt0, 16, 0, s,
+          gr.dbt0));
   }
   if (dx) pe_backward_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, x, b.dE, dx);
   return cudaGetLastError();

@@ -257,6 +257,11 @@ struct DwArgs {
   int transpose;  // 0: C[m, n] (m = X feature, n = Y feature);  1: C[n, m]
   int m_valid;    // X features >= m_valid are not written
   int n_valid;
+  // optional bias gradients from the operand tiles already staged in shared memory (the four epilogue warps
+  // are idle during the main loop): colsum_x[f] += sum over rows of X[:, f] (f relative to the view) for this
+  // CTA's 128 features, colsum_y[f] += sum over rows of Y[:, f] (N <= 128; CTAs with blockIdx.y == 0 only)
+  float* colsum_x;
+  float* colsum_y;
 };
 
 #define DW_STAGES 2
@@ -273,11 +278,13 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const DwArgs g) 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = ring, sB = ring + DW_STAGES * DW_A_BYTES;
+  const bool sum_x = g.colsum_x != nullptr, sum_y = g.colsum_y != nullptr && blockIdx.y == 0 && g.N <= 128;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < DW_STAGES; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 1);
+      // a stage is free once the MMAs have consumed it AND (column sums) the 128 epilogue threads have read it
+      mbar_init(&s_empty[s], (sum_x || sum_y) ? 1 + 128 : 1);
     }
     mbar_init(&s_acc_full, 1);
     mbar_fence_init();
@@ -325,6 +332,60 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const DwArgs g) 
       if (my_tiles > 0) umma::commit(&s_acc_full);
     }
   } else if (my_tiles > 0) {
+    if (sum_x || sum_y) {
+      // ---- column sums of the staged operand tiles while the tensor core multiplies them
+      const int e = tid - 64;                // 0..127
+      const int kb = e >> 3, sub = e & 7;    // 8 threads per 8-feature block, 16 rows each (conflict-free LDS.128)
+      float ax[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ay[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const bool do_y = sum_y && kb < (g.N >> 3);
+      const uint8_t* ring_p = reinterpret_cast<const uint8_t*>(smem_raw) + (ring - smem_u32(smem_raw));
+      for (int i = 0; i < my_tiles; ++i) {
+        const int st = i % DW_STAGES;
+        mbar_wait(&s_full[st], (i / DW_STAGES) & 1);
+        const uint8_t* pa = ring_p + st * DW_A_BYTES + kb * (ACT_R * 16);
+        const uint8_t* pb = ring_p + DW_STAGES * DW_A_BYTES + st * DW_B_BYTES + kb * (ACT_R * 16);
+#pragma unroll 4
+        for (int r = sub; r < ACT_R; r += 8) {
+          if (sum_x) {
+            const uint4 v = *reinterpret_cast<const uint4*>(pa + r * 16);
+            const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __bfloat1622float2(p2[q]);
+              ax[2 * q] += f.x;
+              ax[2 * q + 1] += f.y;
+            }
+          }
+          if (do_y) {
+            const uint4 v = *reinterpret_cast<const uint4*>(pb + r * 16);
+            const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __bfloat1622float2(p2[q]);
+              ay[2 * q] += f.x;
+              ay[2 * q + 1] += f.y;
+            }
+          }
+        }
+        mbar_arrive(&s_empty[st]);
+      }
+      // the 8 threads of a feature block are consecutive lanes
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          ax[q] += __shfl_xor_sync(0xffffffffu, ax[q], o);
+          ay[q] += __shfl_xor_sync(0xffffffffu, ay[q], o);
+        }
+      }
+      if (sub == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (sum_x) atomicAdd(&g.colsum_x[m0 + kb * 8 + q], ax[q]);
+          if (do_y) atomicAdd(&g.colsum_y[kb * 8 + q], ay[q]);
+        }
+      }
+    }
     const int lg = warp & 3;
     const int m = m0 + lg * 32 + lane;  // X feature = accumulator row
     mbar_wait(&s_acc_full, 0);

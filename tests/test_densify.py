@@ -7,6 +7,7 @@ import argparse
 import os
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -101,3 +102,39 @@ def test_fused_densify_and_prune_equals_reference(P, size_thr):
         m.density_thres_param.grad = torch.zeros_like(m.density_thres_param)
         m.optimizer.step()
     assert torch.allclose(a._xyz, b._xyz, rtol=1e-6, atol=1e-6) and torch.equal(a._opacity, b._opacity)
+
+
+@pytest.mark.gpu
+def test_ply_interchange_with_the_reference_model(tmp_path):
+    """SURVEY 8(f)-4 wired to the model: a point cloud written by the reference's own save_ply
+    (gaussian_model_dpsr_dynamic_anchor.py:253-289) is read by checkpoint.load_gaussians_ply, and one written by
+    checkpoint.save_gaussians_ply is read by the reference's load_ply (:296-362), values bit-equal both ways.
+    (`plyfile` itself is not installed: the reference code runs on tools/harness_stubs' minimal stand-in, which
+    only serialises the numpy structured arrays the REFERENCE builds -- names, order and layout are its own.)"""
+    cls = _reference_model_class()
+    if cls is None:
+        pytest.skip("oracle/_ref/dgmesh missing")
+    import checkpoint
+    m = _build(cls, 257, 11, 3.7)
+    m.gaussian_center = torch.tensor([0.1, -0.2, 0.3], device="cuda")
+    m.gaussian_scale = torch.tensor([1.7], device="cuda")
+    m.density_thres_param.data.fill_(0.05)
+    # reference -> ours
+    p1 = str(tmp_path / "a" / "point_cloud" / "iteration_7" / "point_cloud.ply")
+    m.save_ply(p1)
+    d = checkpoint.load_gaussians_ply(p1, max_sh_degree=3)
+    for k, attr in (("xyz", "_xyz"), ("normal", "_normal"), ("features_dc", "_features_dc"),
+                    ("features_rest", "_features_rest"), ("opacity", "_opacity"), ("scaling", "_scaling"),
+                    ("rotation", "_rotation")):
+        assert np.array_equal(d[k], getattr(m, attr).detach().cpu().numpy()), k
+    assert abs(float(d["density_thres"][0]) - 0.05) < 1e-7 and abs(float(d["gaussian_scale"][0]) - 1.7) < 1e-6
+    assert np.allclose(d["gaussian_center"].reshape(-1), [0.1, -0.2, 0.3], atol=1e-7)
+    # ours -> reference
+    p2 = str(tmp_path / "b" / "point_cloud" / "iteration_9" / "point_cloud.ply")
+    checkpoint.save_gaussians_ply(p2, m._xyz, m._normal, m._features_dc, m._features_rest, m._opacity, m._scaling,
+                                  m._rotation, m.density_thres_param, m.gaussian_center, m.gaussian_scale)
+    m2 = cls(3, 32, 0.0, 3.0)
+    m2.load_ply(str(tmp_path / "b"), iteration=9)
+    for attr in ATTRS:
+        assert torch.equal(getattr(m2, attr).detach(), getattr(m, attr).detach()), attr
+    assert torch.allclose(m2.gaussian_center.reshape(-1).float().cpu(), m.gaussian_center.cpu())

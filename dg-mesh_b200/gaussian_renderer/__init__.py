@@ -78,9 +78,14 @@ def render(viewpoint_camera, pc, pipe, bg_color, d_xyz, d_rotation, d_scaling, i
 
 
 def render_batch(cameras, pc, pipe, bg_color, d_xyz, d_rotation, d_scaling, scaling_modifier=1.0):
-    """F cameras over one set of (deformed) Gaussians -> images [F,3,H,W].  The deltas apply to every frame
-    (frames that differ in time are rendered by separate calls / ranks).  Returns the same keys as `render`
-    with a leading frame dimension."""
+    """F training frames in one call -> images [F,3,H,W]; the keys of `render` with a leading frame dimension.
+
+    DG-Mesh deforms the Gaussians by each frame's own time (dgmesh/train.py:157-178): pass `d_xyz`,
+    `d_rotation`, `d_scaling` as [F,N,.] tensors (or lists of F per-frame tensors, e.g. the deformation
+    network's outputs for t_k = fid_k) and every frame renders xyz + d_xyz[k], rotation + d_rotation[k],
+    scaling + d_scaling[k] -- bit-identical to F calls of `render`, with the binning chains of later frames
+    overlapped with the blend kernels of earlier ones.  [N,.] deltas (or 0.0, the warm-up phase) apply to
+    every frame.  Opacity and SH are shared; their gradients are summed over the frames inside the kernels."""
     F, N = len(cameras), pc.get_xyz.shape[0]
     screenspace_points = torch.zeros((F, N, 3), dtype=pc.get_xyz.dtype, requires_grad=True, device="cuda") + 0
     try:
@@ -88,6 +93,18 @@ def render_batch(cameras, pc, pipe, bg_color, d_xyz, d_rotation, d_scaling, scal
     except Exception:
         pass
     sets = [_settings(c, pc, pipe, bg_color, scaling_modifier) for c in cameras]
-    kw = _gaussian_inputs(cameras[0], pc, pipe, d_xyz, d_rotation, d_scaling, False, scaling_modifier, None)
+
+    def per_frame(d):
+        if isinstance(d, (list, tuple)):
+            if len(d) != F:
+                raise ValueError("per-frame deltas: one entry per camera")
+            return torch.stack([x if torch.is_tensor(x) else torch.zeros_like(pc.get_xyz[:, :1]) + x for x in d])
+        return d
+
+    d_xyz, d_rotation, d_scaling = per_frame(d_xyz), per_frame(d_rotation), per_frame(d_scaling)
+    if pipe.compute_cov3D_python or pipe.convert_SHs_python:
+        raise NotImplementedError("render_batch: the python covariance / SH paths are per-camera; use render()")
+    kw = dict(means3D=pc.get_xyz + d_xyz, opacities=pc.get_opacity, scales=pc.get_scaling + d_scaling,
+              rotations=pc.get_rotation + d_rotation, shs=pc.get_features)
     images, radii = BatchGaussianRasterizer(sets)(means2D=screenspace_points, **kw)
     return {"render": images, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii}

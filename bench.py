@@ -92,13 +92,52 @@ def make_inputs(device):
     return sc, cams, dpix
 
 
-def flat_params(sc, device):
+class Exchange:
+    """The step's one collective over the flat gradient buffer: this library's NVSwitch all-reduce kernel
+    (csrc/nvls.cu, buffer in symmetric memory) when the platform has multicast support, else ncclAllReduce."""
+
+    def __init__(self, n, device, world):
+        self.kind, self.handle, self.epoch = "nccl", None, 1
+        n_pad = (n + 3) // 4 * 4
+        self.buf = None
+        if world > 1 and os.environ.get("DGMESH_B200_EXCHANGE", "nvls") == "nvls":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(n_pad, dtype=torch.float32, device=device)
+                h = symm_mem.rendezvous(buf, dist.group.WORLD)
+                if not h.multicast_ptr:
+                    raise RuntimeError("no multicast support")
+                buf.zero_()
+                h.barrier()
+                self.buf, self.handle, self.kind = buf, h, "nvls (own kernel, multimem.ld_reduce / multimem.st)"
+                self.blocks = max(1, min(32, (int(h.signal_pad_size) // 4) // world))
+            except Exception as e:  # recorded in the JSON line
+                self.kind = f"nccl (nvls unavailable: {type(e).__name__}: {e})"
+        if self.buf is None:
+            self.buf = torch.zeros(n_pad, device=device)
+        self.flat = self.buf[:n]
+
+    def allreduce(self):
+        if self.handle is None:
+            dist.all_reduce(self.flat)
+            return
+        import _dgm_lib
+        h = self.handle
+        rc = _dgm_lib.lib().dgx_allreduce_nvls(int(h.multicast_ptr), self.buf.numel(), int(h.signal_pad_ptrs_dev),
+                                               h.rank, h.world_size, self.epoch, 1.0, self.blocks,
+                                               _dgm_lib.stream_ptr())
+        _dgm_lib.check(rc, "dgx_allreduce_nvls")
+        self.epoch += 2
+
+
+def flat_params(sc, device, world=1):
     """Leaves as views of one flat buffer, with .grad views of one flat grad buffer, so the DP
     exchange is a single all-reduce."""
     names = ["means3D", "opacities", "scales", "rotations", "shs"]
     sizes = [sc[n].numel() for n in names]
     flat = torch.empty(sum(sizes), device=device)
-    gflat = torch.zeros_like(flat)
+    ex = Exchange(sum(sizes), device, world)
+    gflat = ex.flat
     leaves, off = {}, 0
     for n, s in zip(names, sizes):
         v = flat[off:off + s].view_as(sc[n])
@@ -107,7 +146,7 @@ def flat_params(sc, device):
         p.grad = gflat[off:off + s].view_as(sc[n])
         leaves[n] = p
         off += s
-    return leaves, gflat
+    return leaves, gflat, ex
 
 
 def make_deltas(sc, device):
@@ -372,7 +411,7 @@ def main():
     sc, cams, dpix = make_inputs(dev)
     dpix = [d.to(dev) for d in dpix]
     deltas_all = make_deltas(sc, dev)
-    leaves, gflat = flat_params(sc, dev)
+    leaves, gflat, exchange = flat_params(sc, dev, world if a.impl == "ours" else 1)
     bg = torch.ones(3, device=dev)
     my_frames = [k for k in range(FRAMES) if k % world == rank]
 
@@ -389,7 +428,7 @@ def main():
         else:
             run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, deltas=deltas_all)
         if world > 1:
-            dist.all_reduce(gflat)  # the one collective of the step
+            exchange.allreduce()  # the one collective of the step
 
     def step_render_only():
         gflat.zero_()
@@ -399,7 +438,7 @@ def main():
         gflat.zero_()
         run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, deltas=deltas_all)
         if world > 1:
-            dist.all_reduce(gflat)
+            exchange.allreduce()
 
     # Optional: capture the step once and replay it as a CUDA graph (parameters, cameras and pixel
     # gradients live at fixed addresses exactly as in a training loop with in-place optimiser updates;
@@ -433,12 +472,25 @@ def main():
         sampler.start()
     ms = timed(timed_step, a.steps, a.warmup, world)
     clocks = sampler.stop() if rank == 0 else None
+    if use_graph:
+        # graph replay cannot wait for the status words (no host interaction inside a graph): prove that no frame
+        # overflowed its instance workspace by comparing the replayed gradient with an eager step's
+        graph.replay()
+        torch.cuda.synchronize()
+        g_replay = gflat.clone()
+        step()
+        torch.cuda.synchronize()
+        err = float((g_replay - gflat).abs().max() / (gflat.abs().max() + 1e-30))
+        graph_note = f"replay vs eager gradient max-norm difference {err:.2e}"
+        assert err < 1e-3, graph_note
     value = FRAMES * a.steps / (ms * 1e-3)
     breakdown = None
     if world > 1 and ours:
+        nccl_probe = torch.zeros_like(gflat)
         breakdown = {"render_only_ms": timed(step_render_only, a.steps, 2, world) / a.steps,
-                     "allreduce_only_ms": timed(lambda: dist.all_reduce(gflat), a.steps, 2, world) / a.steps,
-                     "allreduce_bytes": gflat.numel() * 4}
+                     "allreduce_only_ms": timed(exchange.allreduce, a.steps, 2, world) / a.steps,
+                     "nccl_allreduce_only_ms": timed(lambda: dist.all_reduce(nccl_probe), a.steps, 2, world) / a.steps,
+                     "allreduce_bytes": gflat.numel() * 4, "exchange": exchange.kind}
 
     # ---- e2e leg: host buffers, copies inside the timed region
     feed = HostFeed(cams, my_frames, dev)
@@ -455,7 +507,7 @@ def main():
                           (lambda c, i=i: feed.pixel_grad(c, i))) for i, k in enumerate(my_frames)}
             run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged, deltas=deltas_all)
         if world > 1:
-            dist.all_reduce(gflat)
+            exchange.allreduce()
         feed.finish(gflat.sum())
 
     e2e_steps = a.steps
@@ -477,7 +529,7 @@ def main():
                           (lambda c, i=i: feed1.pixel_grad(c, i))) for i, k in enumerate(my_frames)}
             run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged, deltas=deltas_all)
             if world > 1:
-                dist.all_reduce(gflat)
+                exchange.allreduce()
             feed1.finish(gflat.sum())
 
         ms_single_e2e = timed(step_single_e2e, a.steps, 3, world)
@@ -598,7 +650,12 @@ def main():
             import train_step as ts
             torch.cuda.empty_cache()
             S = ts.build("ours", 200_000, 288, dev, azimuth_deg=360.0 * rank / world)   # same seed: replicated parameters
-            fg = dp.FlatGrad(S.params)
+            try:
+                fg = dp.NvlsFlatGrad(S.params)       # this library's NVSwitch all-reduce
+                fg_kind = "nvls (own kernel)"
+            except Exception as e:
+                fg = dp.FlatGrad(S.params)
+                fg_kind = f"nccl ({type(e).__name__}: {e})"
 
             def dp_step():
                 fg.zero()
@@ -614,6 +671,7 @@ def main():
             out["train_step_dp"] = {"config": "C4: full train step (200k Gaussians, grid 288), 1 frame per rank, t_k = k/N",
                                     "ms_per_step": ms_dp, "ms_without_allreduce": ms_local,
                                     "frames_per_s": world / (ms_dp * 1e-3), "allreduce_bytes": fg.flat.numel() * 4,
+                                    "exchange": fg_kind,
                                     "scaling": "weak"}
             del S, fg
         except Exception as e:

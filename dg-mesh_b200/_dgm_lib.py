@@ -74,6 +74,7 @@ SIGNATURES = {
     "dgd_plan": (c_int, [c_int, P, P, P, P, c_float, c_float, c_float, c_float, c_int, c_float, P, c_size_t, P, P]),
     "dgd_split_stds": (c_int, [c_int, P, P, c_size_t, P, P]),
     "dgd_apply": (c_int, [c_int, c_int, P, P, P, P, c_size_t, P]),
+    "dgx_allreduce_nvls": (c_int, [P, c_size_t, P, c_int, c_int, ctypes.c_uint32, c_float, c_int, P]),
     "dgm_profile_enable": (c_int, [c_int]),
     "dgloss_workspace_size": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "dgloss_forward": (c_int, [c_int, c_int, P, P, c_float, c_int, P, P, c_size_t, P]),

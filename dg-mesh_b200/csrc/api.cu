@@ -9,6 +9,7 @@
 #include "mlp_kernels.h"
 #include "densify_kernels.h"
 #include "meshrast_kernels.h"
+#include "nvls_kernels.h"
 
 #include <string.h>
 #include <stdlib.h>
@@ -765,6 +766,15 @@ int dgd_apply(int P, int n_fields, const DgdField* fields_host, const float* rot
   }
   if (cols > 64) return bad("dgd_apply: more than 64 parameter columns");
   return check(dgm::launch_densify_apply(P, t, samples, ws, (cudaStream_t)stream));
+}
+
+int dgx_allreduce_nvls(float* multicast_ptr, size_t n_floats, void* signal_pads_dev, int rank, int world,
+                       uint32_t epoch, float scale, int blocks, void* stream) {
+  if (!multicast_ptr || !signal_pads_dev || world < 1 || rank < 0 || rank >= world || blocks < 1 || (n_floats & 3) ||
+      ((uintptr_t)multicast_ptr & 15) || epoch == 0)
+    return bad("dgx_allreduce_nvls: bad argument");
+  return check(dgm::launch_nvls_allreduce(multicast_ptr, n_floats, (uint32_t* const*)signal_pads_dev, rank, world,
+                                          epoch, scale, blocks, (cudaStream_t)stream));
 }
 
 // ---- early notification objects: an event + a device-mapped pinned status mirror.  These are the

@@ -7,8 +7,15 @@ NVLink on the B200 box, gloo in the CPU tests) of a single flat fp32 buffer hold
 canonical-Gaussian parameters followed by the MLP parameters.  Batch of one frame per step -> no
 collective at all.  Densification statistics need the same reduction so all ranks prune identically
 (gaussian_model_dpsr_dynamic_anchor.py:679-682)."""
+import os
+import sys
+
 import torch
 import torch.distributed as dist
+
+_root = os.path.dirname(os.path.abspath(__file__))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
 
 
 def shard_frames(n_frames, rank, world):
@@ -78,6 +85,66 @@ class FlatGrad:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             if average:
                 self.flat.div_(dist.get_world_size(group))
+        return self.flat
+
+
+class NvlsFlatGrad(FlatGrad):
+    """`FlatGrad` whose buffer lives in symmetric memory behind an NVSwitch MULTICAST mapping, all-reduced by
+    this library's own kernel (csrc/nvls.cu: the switch performs the reduction -- `multimem.ld_reduce` of this
+    rank's slice, `multimem.st` of the result to every replica; one launch, two flag barriers) instead of
+    ncclAllReduce.  At the sizes of this path (24-60 MB) the NCCL call is latency-bound; see DESIGN.md 5.
+
+    Needs a NCCL process group (for the rendezvous only) on GPUs joined by NVSwitch; raises if the platform has
+    no multicast support (use `FlatGrad` there).  torch's symmetric-memory allocator is plumbing: it provides
+    the memory, the multicast address and the signal pads; the collective itself is ours."""
+
+    BLOCKS = 32
+
+    def __init__(self, params, group=None):
+        self.group = group
+        self._epoch = 1
+        self._handle = None
+        super().__init__(params)
+
+    def rebuild(self, params):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGrad: no parameter requires grad")
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("NvlsFlatGrad needs an initialised process group (NCCL) for the rendezvous")
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        n_pad = (n + 3) // 4 * 4
+        group = self.group if self.group is not None else dist.group.WORLD
+        buf = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)
+        self._handle = symm_mem.rendezvous(buf, group)
+        if not self._handle.has_multicast_support() if callable(getattr(self._handle, "has_multicast_support", None)) \
+                else not self._handle.multicast_ptr:
+            raise RuntimeError("NvlsFlatGrad: no NVSwitch multicast support on this platform; use FlatGrad (NCCL)")
+        buf.zero_()
+        self._buf = buf
+        self.flat = buf[:n]
+        self.offsets, self.shapes, off = [], [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            self.shapes.append(tuple(p.shape))
+            off += p.numel()
+        self._bind(copy=False)
+        pad_words = int(self._handle.signal_pad_size) // 4
+        self._blocks = max(1, min(self.BLOCKS, pad_words // max(1, self._handle.world_size)))
+        self._handle.barrier()      # everyone's buffer and pads exist (and are zero) before the first kernel
+
+    def allreduce(self, average=True, group=None):
+        import _dgm_lib
+        self._bind(copy=True)
+        h = self._handle
+        world = h.world_size
+        rc = _dgm_lib.lib().dgx_allreduce_nvls(int(h.multicast_ptr), self._buf.numel(), int(h.signal_pad_ptrs_dev),
+                                               h.rank, world, self._epoch, (1.0 / world) if average else 1.0,
+                                               self._blocks, _dgm_lib.stream_ptr())
+        _dgm_lib.check(rc, "dgx_allreduce_nvls")
+        self._epoch += 2
         return self.flat
 
 

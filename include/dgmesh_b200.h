@@ -473,6 +473,21 @@ int dgd_apply(int P, int n_fields, const DgdField* fields_host, const float* rot
               void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Data-parallel exchange: in-place all-reduce (sum, then * scale) of ONE flat fp32 buffer
+ * that lives in symmetric memory mapped through an NVSwitch multicast object -- the reduction is done BY THE
+ * SWITCH (multimem.ld_reduce of this rank's slice, multimem.st of the result to every replica), one kernel,
+ * two flag barriers across the ranks.  No reference counterpart (the reference is single-GPU); replaces the
+ * ncclAllReduce this path would otherwise issue.
+ *   multicast_ptr   the multicast (NVLS) address of the buffer; n_floats a multiple of 4, buffer 16-B aligned
+ *   signal_pads_dev device array of `world` pointers to the ranks' signal pads (uint32, symmetric memory),
+ *                   each at least `blocks * world` words, zero before the first call
+ *   epoch           starts at 1 and must advance by 2 per call on all ranks alike (flags are never reset)
+ *   blocks          CTAs (<= signal-pad words / world); the same value on every rank
+ * ------------------------------------------------------------------------ */
+int dgx_allreduce_nvls(float* multicast_ptr, size_t n_floats, void* signal_pads_dev, int rank, int world,
+                       uint32_t epoch, float scale, int blocks, void* stream);
+
+/* ------------------------------------------------------------------------
  * Measurement hooks (bench.py roofline leg).  Off by default.  When enabled the
  * library records a CUDA event pair around each of its kernels ON THE LAUNCHING
  * STREAM; dgm_profile_read synchronises those events (the only call in this

@@ -36,22 +36,22 @@ def _worker(rank, world, port, n_frames, out):
     acc, den, rad = torch.full((50, 1), float(rank + 1)), torch.full((50, 1), 1.0), torch.arange(50.) * (rank + 1)
     dp.sync_densification_stats(acc, den, rad)
     if rank == 0:
-        out.put((flat, acc, den, rad))
+        torch.save((flat, acc, den, rad), out)      # a file, not a multiprocessing queue (spawn + pipes proved flaky)
     dist.destroy_process_group()
 
 
-def test_allreduced_gradient_equals_sum_of_frame_gradients():
+def test_allreduced_gradient_equals_sum_of_frame_gradients(tmp_path):
     n_frames, world = 8, 2
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
+    out = str(tmp_path / "rank0.pt")
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, out)) for r in range(world)]
     for p in procs:
         p.start()
-    flat, acc, den, rad = q.get(timeout=120)
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
+    flat, acc, den, rad = torch.load(out)
     torch.manual_seed(0)
     params = [torch.randn(50, 3, requires_grad=True), torch.randn(7, 3, requires_grad=True)]
     fg = dp.FlatGrad(params)

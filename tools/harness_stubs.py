@@ -177,10 +177,18 @@ def _make_pytorch3d():
     pkg.__name__ = "pytorch3d"
     ops = types.ModuleType("pytorch3d.ops")
 
+    import collections
+    KNN = collections.namedtuple("KNN", "dists idx knn")
+
     def knn_points(p1, p2, K=1, **kw):
-        d = torch.cdist(p1, p2) ** 2
-        dists, idx = d.topk(K, dim=-1, largest=False)
-        return types.SimpleNamespace(dists=dists, idx=idx, knn=None)
+        """exact brute force in chunks (pytorch3d.ops.knn_points returns squared distances)"""
+        dists, idxs = [], []
+        for chunk in p1[0].split(4096):
+            d = torch.cdist(chunk[None], p2) ** 2
+            dd, ii = d.topk(K, dim=-1, largest=False)
+            dists.append(dd)
+            idxs.append(ii)
+        return KNN(torch.cat(dists, 1), torch.cat(idxs, 1), None)
 
     ops.knn_points = knn_points
     return pkg, ops

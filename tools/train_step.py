@@ -224,5 +224,18 @@ if __name__ == "__main__":
     ap.add_argument("--gaussians", type=int, default=200_000)
     ap.add_argument("--grid", type=int, default=288)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--profile", action="store_true",
+                    help="two full steps of this implementation only, bracketed by cudaProfilerStart/Stop around the "
+                         "second one (for `ncu --profile-from-start off --metrics gpu__time_duration.sum`)")
     a = ap.parse_args()
+    if a.profile:
+        S = build("ours", a.gaussians, a.grid, torch.device("cuda"))
+        full_step(S)
+        full_step(S)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        full_step(S)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        sys.exit(0)
     print(json.dumps(measure(a.gaussians, a.grid, a.steps)))

@@ -521,6 +521,12 @@ __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __rest
 // (semantics of renderCUDA, forward.cu:261-374).
 #define RB 256  // records per batch (== reference BLOCK_SIZE staging granularity)
 
+#ifdef DGM_COUNT_PAIRS
+// diagnostic build only (tools/pair_stats.py): [0] (warp, Gaussian) pairs evaluated after the cull,
+// [1] those in which at least one lane blended the Gaussian, [2] (warp, Gaussian) pairs before the cull
+__device__ unsigned long long g_dbg_pairs[4];
+#endif
+
 __global__ void __launch_bounds__(256, 5) render_fwd_kernel(const uint2* __restrict__ ranges,
                                                          const uint32_t* __restrict__ tile_order,
                                                          const float4* __restrict__ inst_geo,
@@ -599,6 +605,9 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(const uint2* __restr
       }
       keep[k] = __ballot_sync(0xffffffffu, kp);
     }
+#ifdef DGM_COUNT_PAIRS
+    if (lane == 0) atomicAdd(&g_dbg_pairs[2], (unsigned long long)nb);
+#endif
     // ---- blend the survivors front to back, two records per iteration: the quadratic
     // form of both is evaluated with packed fp32x2 instructions (FADD2/FMUL2/FFMA2, new on
     // sm_100), the order-dependent transmittance update stays scalar.  The operation
@@ -628,11 +637,17 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(const uint2* __restr
         float2 m3 = __fmul2_rn(dx, make_float2(coA.y, coB.y));
         m3 = __fmul2_rn(dy, m3);
         const float2 npow = __ffma2_rn(sq, make_float2(0.5f, 0.5f), m3);  // = -power (exactly)
+#ifdef DGM_COUNT_PAIRS
+        const uint32_t lc_before = last_contributor;
+#endif
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const float np = q ? npow.y : npow.x;
           const float opac = q ? coB.w : coA.w;
           const int j = q ? jB : jA;
+#ifdef DGM_COUNT_PAIRS
+          const uint32_t lc0 = last_contributor;
+#endif
           if ((q == 0 || two) && !done && !(np < 0.0f)) {  // reference: if (power > 0) continue
             const float alpha = fminf(0.99f, __fmul_rn(opac, expf(-np)));
             if (!(alpha < 1.0f / 255.0f)) {
@@ -649,7 +664,19 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(const uint2* __restr
               }
             }
           }
+#ifdef DGM_COUNT_PAIRS
+          if (q == 0 || two) {
+            const bool any = __any_sync(0xffffffffu, last_contributor != lc0);
+            if (lane == 0) {
+              atomicAdd(&g_dbg_pairs[0], 1ull);
+              if (any) atomicAdd(&g_dbg_pairs[1], 1ull);
+            }
+          }
+#endif
         }
+#ifdef DGM_COUNT_PAIRS
+        (void)lc_before;
+#endif
       }
     }
   }
@@ -662,6 +689,20 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(const uint2* __restr
     out_color[2 * HW + pix_id] = C2 + T * bg_color[2];
   }
 }
+
+#ifdef DGM_COUNT_PAIRS
+}  // namespace dgm
+extern "C" int dgm_debug_pair_counters(unsigned long long* out4, int reset) {
+  cudaDeviceSynchronize();
+  if (out4) cudaMemcpyFromSymbol(out4, dgm::g_dbg_pairs, sizeof(unsigned long long) * 4);
+  if (reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(dgm::g_dbg_pairs, z, sizeof(z));
+  }
+  return 0;
+}
+namespace dgm {
+#endif
 
 // frustum test only (rasterizer_impl.cu:54-66)
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,

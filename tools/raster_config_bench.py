@@ -17,7 +17,10 @@ import torch  # noqa: E402
 import synth  # noqa: E402
 import util  # noqa: E402
 
-CONFIGS = {"c2": (100_000, 800, 800), "c5": (500_000, 1920, 1080)}
+CONFIGS = {"c2": (100_000, 800, 800), "c5": (500_000, 1920, 1080),
+           # an OBJECT-shaped scene (what DG-Mesh trains on): 200k Gaussians on a thick shell of radius 0.6 that
+           # covers ~14 % of the image -> thousands of instances per tile, narrow per-tile depth ranges
+           "object": (200_000, 800, 800)}
 
 
 def run(dgr, sc, cams, dpix, bg, W, H, steps):
@@ -56,6 +59,10 @@ if __name__ == "__main__":
     n, W, H = CONFIGS[a.config]
     dev = torch.device("cuda")
     sc = synth.gaussian_scene(n=n, seed=0, device=dev)
+    if a.config == "object":
+        g = torch.Generator().manual_seed(3)
+        d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1)
+        sc["means3D"] = (d * 0.6 + 0.01 * torch.randn(n, 3, generator=g)).to(dev)
     cams = [synth.look_at_camera(azimuth_deg=45.0 * k, elevation_deg=20.0, radius=4.0, width=W, height=H,
                                  fovx=2 * math.atan(math.tan(0.6911 / 2) * W / H), fovy=0.6911, device=dev)
             for k in range(8)]
@@ -65,6 +72,13 @@ if __name__ == "__main__":
     out = {"config": a.config, "gaussians": n, "width": W, "height": H, "views": 8}
     ms = run(ours, sc, cams, dpix, bg, W, H, a.steps)
     out["ours_ms_per_frame"], out["ours_frames_per_s"] = ms, 1e3 / ms
+    import _dgm_lib
+    _dgm_lib.lib().dgm_profile_enable(1)
+    run(ours, sc, cams[:1], dpix, bg, W, H, 1)
+    out["ours_kernel_us_one_frame"] = {k: round(v * 1e3, 1) for k, v in _dgm_lib.profile_read().items()}
+    _dgm_lib.lib().dgm_profile_enable(0)
+    st = ours._Notify.get(dev.index).words
+    out["num_rendered"], out["max_tile_length"] = int(st[0]), int(st[2])
     ref = util.load_reference_rasterizer()
     if ref is not None:
         msr = run(ref, sc, cams, dpix, bg, W, H, a.steps)

@@ -181,6 +181,11 @@ def run(a):
     cwd = os.getcwd()
     os.chdir(REF_TREE)
     err = None
+    prof = None
+    if os.environ.get("HARNESS_CPROFILE"):
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     try:
         runpy.run_path(os.path.join(REF_TREE, "train.py"), run_name="__main__")
     except _Stop:
@@ -190,6 +195,10 @@ def run(a):
         err = f"{type(e).__name__}: {e} @ " + " <- ".join(
             f"{os.path.basename(f.filename)}:{f.lineno}" for f in traceback.extract_tb(e.__traceback__)[-4:])
     finally:
+        if prof is not None:
+            import pstats
+            prof.disable()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
         os.chdir(cwd)
         sys.stdout = real_stdout
         torch.Tensor.backward = orig_backward

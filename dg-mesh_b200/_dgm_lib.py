@@ -30,12 +30,12 @@ SIGNATURES = {
     "dgm_notify_destroy": (c_int, [P]),
     "dgr_forward": (c_int, [c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_float, P, P, P, P, P,
                             c_float, c_float, c_int, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P, P,
-                            c_float, c_float, P]),
+                            c_float, c_float, c_int, P]),
     "dgr_backward": (c_int, [c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P,
                              c_float, c_float, P, P, P, c_int64, P, P, P, P, P, P, P, P, P, P, P, P]),
     "dgr_forward_batch": (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_float, P, P, c_int,
                                   P, P, P, P, P, c_int, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P, P,
-                                  c_float, c_float, c_int, P]),
+                                  c_float, c_float, c_int, c_int, P]),
     "dgr_backward_batch": (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, c_float, P, P, c_int,
                                    P, P, P, P, P, P, P, c_size_t, P, c_size_t, c_int64, P, c_size_t, P, P, P, P, P, P,
                                    P, P, P, c_int, P]),

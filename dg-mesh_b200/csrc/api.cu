@@ -108,7 +108,7 @@ int dgr_forward(int P, int D, int M, const float* background, int W, int H, cons
                 const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, float* out_color, int* radii,
                 void* geom_ws, size_t geom_bytes, void* binning_ws, size_t binning_bytes, int64_t R_cap, void* img_ws,
                 size_t img_bytes, int32_t* status, int32_t* status_host, void* status_event, float depth_hint_lo,
-                float depth_hint_hi, void* stream) {
+                float depth_hint_hi, int max_tile_hint, void* stream) {
   if (P < 0 || W <= 0 || H <= 0 || R_cap < 0) return bad("dgr_forward: negative size");
   if (!background || !viewmatrix || !projmatrix || !cam_pos || !out_color || !status)
     return bad("dgr_forward: null required pointer");
@@ -144,7 +144,7 @@ int dgr_forward(int P, int D, int M, const float* background, int W, int H, cons
   a.out_color = out_color; a.radii = radii;
   a.geom_ws = geom_ws; a.binning_ws = binning_ws; a.img_ws = img_ws; a.R_cap = R_cap; a.status = status;
   a.status_host = status_host; a.status_event = (cudaEvent_t)status_event;
-  a.hint_lo = depth_hint_lo; a.hint_hi = depth_hint_hi;
+  a.hint_lo = depth_hint_lo; a.hint_hi = depth_hint_hi; a.hint_max_tile = max_tile_hint;
   return check(dgm::launch_forward(a, (cudaStream_t)stream));
 }
 
@@ -227,7 +227,7 @@ dgm::FwdArgs fwd_args(int P, int D, int M, const float* background, int W, int H
                       const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
                       float tan_fovy, int prefiltered, float* out_color, int* radii, void* geom_ws, void* binning_ws,
                       int64_t R_cap, void* img_ws, int32_t* status, int32_t* status_host, float hint_lo,
-                      float hint_hi) {
+                      float hint_hi, int hint_max_tile) {
   dgm::FwdArgs a;
   a.P = P; a.D = D; a.M = M; a.background = background; a.W = W; a.H = H;
   a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
@@ -237,6 +237,7 @@ dgm::FwdArgs fwd_args(int P, int D, int M, const float* background, int W, int H
   a.out_color = out_color; a.radii = radii;
   a.geom_ws = geom_ws; a.binning_ws = binning_ws; a.img_ws = img_ws; a.R_cap = R_cap; a.status = status;
   a.status_host = status_host; a.status_event = nullptr; a.hint_lo = hint_lo; a.hint_hi = hint_hi;
+  a.hint_max_tile = hint_max_tile;
   return a;
 }
 }  // namespace
@@ -248,7 +249,8 @@ int dgr_forward_batch(int F, int P, int D, int M, const float* background, int W
                       const float* tan_fovx_host, const float* tan_fovy_host, int prefiltered, float* out_color,
                       int* radii, void* geom_ws, size_t geom_stride, void* binning_ws, size_t binning_stride,
                       int64_t R_cap, void* img_ws, size_t img_stride, int32_t* status, int32_t* status_host,
-                      void* status_event, float depth_hint_lo, float depth_hint_hi, int n_streams, void* stream) {
+                      void* status_event, float depth_hint_lo, float depth_hint_hi, int max_tile_hint, int n_streams,
+                      void* stream) {
   if (F <= 0 || !tan_fovx_host || !tan_fovy_host || !viewmatrices || !projmatrices || !cam_poses)
     return bad("dgr_forward_batch: bad argument");
   size_t gb, bb, ib;
@@ -277,7 +279,7 @@ int dgr_forward_batch(int F, int P, int D, int M, const float* background, int W
                        (char*)geom_ws + f * geom_stride, geom_stride, (char*)binning_ws + f * binning_stride,
                        binning_stride, R_cap, (char*)img_ws + f * img_stride, img_stride,
                        status + f * DGR_STATUS_WORDS, status_host ? status_host + f * DGR_STATUS_WORDS : nullptr,
-                       (f == F - 1) ? status_event : nullptr, depth_hint_lo, depth_hint_hi, main_s);
+                       (f == F - 1) ? status_event : nullptr, depth_hint_lo, depth_hint_hi, max_tile_hint, main_s);
     return rc;
   }
   if (!background || !out_color || !status || !means3D || !opacities) return bad("dgr_forward_batch: null required pointer");
@@ -303,7 +305,7 @@ int dgr_forward_batch(int F, int P, int D, int M, const float* background, int W
         projmatrices + 16 * f, cam_poses + 3 * f, tan_fovx_host[f], tan_fovy_host[f], prefiltered,
         out_color + (size_t)f * 3 * W * H, radii ? radii + (size_t)f * P : nullptr, (char*)geom_ws + f * geom_stride,
         (char*)binning_ws + f * binning_stride, R_cap, (char*)img_ws + f * img_stride, status + f * DGR_STATUS_WORDS,
-        status_host ? status_host + f * DGR_STATUS_WORDS : nullptr, depth_hint_lo, depth_hint_hi);
+        status_host ? status_host + f * DGR_STATUS_WORDS : nullptr, depth_hint_lo, depth_hint_hi, max_tile_hint);
     e = dgm::launch_binning(a, bs->hi[i]);
     cudaEventRecord(bs->ready[i], bs->hi[i]);
     cudaStreamWaitEvent(lo, bs->ready[i], 0);

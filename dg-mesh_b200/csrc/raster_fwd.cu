@@ -407,10 +407,22 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, GeomWS g, const uin
 }
 
 // ======================================================= tile sort+pack ====
-// One CTA per tile: sort the segment by (depth bits, gaussian id) with a normalised
-// bitonic network (all comparators ascending, so virtual +inf padding never moves and
-// any length works), then write point_list and the packed blend records.
-#define SORT_SMEM_KEYS 6016  // 47 KB static shared memory
+// One CTA per tile: the segment is already partitioned into DEPTH_BUCKETS depth-ordered blocks (scatter
+// left each block's END in hist); sort every block by (depth bits, gaussian id) -- which is exactly the
+// order the reference's stable sort on (tile | depth) yields -- then write point_list and the packed blend
+// records.  Block sizes vary by orders of magnitude between scenes: a spread-out scene (C2) has ~1 key per
+// block, an object that fills a seventh of the image (what DG-Mesh trains on) has thousands of keys per
+// tile in a few dozen blocks.  Three regimes, chosen per BLOCK, not per tile:
+//   <= 48 keys      insertion sort by the block's own thread
+//   <= 2048 keys    warp-cooperative bitonic network (normalised: all comparators ascending, so virtual
+//                   +inf padding never moves and any length works); the 8 warps take such blocks round-robin
+//   larger          the whole CTA sorts the block
+// Keys are staged in dynamic shared memory when the segment fits (capacity chosen by the host from the
+// previous frame's longest tile, status word 2), else sorted in place in global memory (L2-resident).
+#define SORT_SMEM_KEYS 6016       // default capacity: 47 KB
+#define SORT_SMEM_KEYS_BIG 24576  // dense scenes: 192 KB, one CTA per SM
+#define BLOCK_SORT_MAX 48         // longest block one thread sorts by insertion
+#define WARP_SORT_MAX 2048        // longest block one warp sorts
 
 __device__ __forceinline__ void cmpswap(unsigned long long* a, uint32_t lo, uint32_t hi, uint32_t n) {
   if (hi < n) {
@@ -422,6 +434,9 @@ __device__ __forceinline__ void cmpswap(unsigned long long* a, uint32_t lo, uint
   }
 }
 
+// normalised bitonic sort of a[0..n) by `nthreads` cooperating threads (WARP: one warp, __syncwarp between
+// steps; otherwise the whole CTA, __syncthreads)
+template <bool WARP>
 __device__ __forceinline__ void bitonic_sort_any(unsigned long long* a, uint32_t n, uint32_t tid, uint32_t nthreads) {
   if (n < 2) return;
   const uint32_t lm = 32 - __clz(n - 1);  // m = 1 << lm = next power of two >= n
@@ -433,54 +448,46 @@ __device__ __forceinline__ void bitonic_sort_any(unsigned long long* a, uint32_t
       const uint32_t off = i & (hk - 1), base = (i >> (lk - 1)) << lk;
       cmpswap(a, base + off, base + (hk << 1) - 1 - off, n);
     }
-    __syncthreads();
+    if (WARP) __syncwarp(); else __syncthreads();
     for (uint32_t j = hk >> 1; j >= 1; j >>= 1) {
       for (uint32_t i = tid; i < half; i += nthreads) {
         const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
         cmpswap(a, lo, lo + j, n);
       }
-      __syncthreads();
+      if (WARP) __syncwarp(); else __syncthreads();
     }
   }
 }
-
-#define BLOCK_SORT_MAX 48  // longest (tile, bucket) block one thread sorts by insertion
 
 __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __restrict__ ranges,
                                                              unsigned long long* __restrict__ keys,
                                                              const uint32_t* __restrict__ hist, GeomWS g,
                                                              const float* __restrict__ colors_precomp, BinWS b,
-                                                             const int32_t* __restrict__ status) {
-  __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
-  __shared__ uint32_t s_maxblock;
+                                                             const int32_t* __restrict__ status, uint32_t smem_keys) {
+  extern __shared__ __align__(16) unsigned long long s_keys[];
+  __shared__ uint32_t s_end[DEPTH_BUCKETS + 1];  // s_end[k] = start of block k, s_end[k + 1] = its end
   pdl_wait();
   pdl_launch();
   if (status[1]) return;
   const uint2 range = ranges[blockIdx.x];
   const uint32_t n = range.y - range.x;
   if (n == 0) return;
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   unsigned long long* seg = keys + range.x;
   unsigned long long* a;
-  if (n <= SORT_SMEM_KEYS) {
+  if (n <= smem_keys) {
     for (uint32_t i = tid; i < n; i += 256) s_keys[i] = seg[i];
     a = s_keys;
   } else {
     a = seg;  // rare: work on the segment in place in global memory (L2-resident)
   }
   // block tid of this tile: [bstart, bend) relative to the segment (scatter left the block END in hist)
-  const uint32_t* row = hist + (size_t)blockIdx.x * DEPTH_BUCKETS;
-  const uint32_t bend = row[tid];
-  const uint32_t bstart = tid ? row[tid - 1] : 0u;
-  if (tid == 0) s_maxblock = 0;
+  const uint32_t bend = hist[(size_t)blockIdx.x * DEPTH_BUCKETS + tid];
+  s_end[tid + 1] = bend;
+  if (tid == 0) s_end[0] = 0;
   __syncthreads();
-  uint32_t mx = bend - bstart;
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((tid & 31) == 0) atomicMax(&s_maxblock, mx);
-  __syncthreads();
-  if (s_maxblock <= BLOCK_SORT_MAX) {
-    // the buckets are already in depth order: sort each short block on its own
+  const uint32_t bstart = s_end[tid];
+  if (bend - bstart <= BLOCK_SORT_MAX) {
     for (uint32_t i = bstart + 1; i < bend; ++i) {
       const unsigned long long key = a[i];
       uint32_t j = i;
@@ -490,10 +497,20 @@ __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __rest
       }
       a[j] = key;
     }
-    __syncthreads();
-  } else {
-    bitonic_sort_any(a, n, tid, 256);
   }
+  __syncwarp();
+  // medium blocks: one warp each
+  for (uint32_t k = wid; k < DEPTH_BUCKETS; k += 8) {
+    const uint32_t s0 = s_end[k], len = s_end[k + 1] - s0;
+    if (len > BLOCK_SORT_MAX && len <= WARP_SORT_MAX) bitonic_sort_any<true>(a + s0, len, lane, 32);
+  }
+  __syncthreads();
+  // huge blocks: the whole CTA (uniform loop: every thread sees the same sizes)
+  for (uint32_t k = 0; k < DEPTH_BUCKETS; ++k) {
+    const uint32_t s0 = s_end[k], len = s_end[k + 1] - s0;
+    if (len > WARP_SORT_MAX) bitonic_sort_any<false>(a + s0, len, tid, 256);
+  }
+  __syncthreads();
   const float* colors = colors_precomp ? colors_precomp : g.rgb;
   for (uint32_t i = tid; i < n; i += 256) {
     const unsigned long long k = a[i];
@@ -763,8 +780,20 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
              (const uint32_t*)im.depth_range, b.keys, gx, gy, (const int32_t*)a.status, use_hint, a.hint_lo, a.hint_hi);
   g_prof.end(2, s);
   g_prof.begin(3, s);
-  launch_pdl(tile_sort_pack_kernel, dim3(T), dim3(256), 0, s, (const uint2*)im.ranges, b.keys,
-             (const uint32_t*)im.hist, g, a.colors_precomp, b, (const int32_t*)a.status);
+  {
+    // shared-memory capacity of the per-tile sort: the default holds 6016 keys at four CTAs per SM; a frame
+    // whose longest tile list (hinted by the previous frame) is longer gets 24576 keys at one CTA per SM
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(tile_sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SORT_SMEM_KEYS_BIG * (int)sizeof(unsigned long long));
+      attr = true;
+    }
+    const uint32_t cap = (a.hint_max_tile > SORT_SMEM_KEYS) ? SORT_SMEM_KEYS_BIG : SORT_SMEM_KEYS;
+    launch_pdl(tile_sort_pack_kernel, dim3(T), dim3(256), cap * sizeof(unsigned long long), s,
+               (const uint2*)im.ranges, b.keys, (const uint32_t*)im.hist, g, a.colors_precomp, b,
+               (const int32_t*)a.status, cap);
+  }
   g_prof.end(3, s);
   return cudaGetLastError();
 }

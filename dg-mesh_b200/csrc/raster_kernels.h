@@ -24,6 +24,7 @@ struct FwdArgs {
   // depth range of an earlier frame (hint_hi > hint_lo enables the fused preprocess + count)
   int32_t* status_host;
   float hint_lo, hint_hi;
+  int hint_max_tile;         // longest per-tile list of an earlier frame (status word 2), 0: unknown
   cudaEvent_t status_event;  // recorded right after the tile scan (may be null)
 };
 

@@ -84,47 +84,48 @@ class _Sizing:
     densification), the enqueued kernels skip themselves and the forward is re-run with the right
     capacity before the caller ever sees the image: results are exact in every case, no exception,
     no background-only frame."""
-    hint = {}       # (device, W, H) -> [R capacity, depth lo, depth hi]
+    hint = {}       # (device, W, H) -> [R capacity, depth lo, depth hi, longest tile list]
 
     @classmethod
     def lookup(cls, key, P):
         h = cls.hint.get(key)
         if h is None:
-            return _round_cap(max(4 * P, 1 << 18)), 0.0, 0.0
-        return h[0], h[1], h[2]
+            return _round_cap(max(4 * P, 1 << 18)), 0.0, 0.0, 0
+        return h[0], h[1], h[2], h[3]
 
     @classmethod
-    def update(cls, key, R, lo, hi):
+    def update(cls, key, R, lo, hi, max_tile=0):
         h = cls.hint.get(key)
         if h is None:
             if len(cls.hint) >= 64:      # bounded: image shapes seen by one process
                 cls.hint.clear()
-            h = cls.hint[key] = [0, 0.0, 0.0]
+            h = cls.hint[key] = [0, 0.0, 0.0, 0]
         h[0] = max(h[0], _grow(R))
+        h[3] = int(max_tile)
         if hi > lo:
             h[1], h[2] = lo, hi
 
 
 def _run_sized(enqueue, key, P, dev_index, F=1):
-    """enqueue(R_cap, notify, lo, hi) -> outputs.  Returns (outputs, R of the largest frame)."""
-    cap, lo, hi = _Sizing.lookup(key, P)
+    """enqueue(R_cap, notify, lo, hi, max_tile) -> outputs.  Returns (outputs, R of the largest frame)."""
+    cap, lo, hi, mt = _Sizing.lookup(key, P)
     if torch.cuda.is_current_stream_capturing():
         # CUDA-graph capture: no host-side waiting; the capacity comes from the eager warm-up and an
         # overflow (status word 1) would replay as a background frame -- callers of graph replay check
         # `last_status()`; bench.py does
-        return enqueue(cap, None, lo, hi), None
+        return enqueue(cap, None, lo, hi, mt), None
     nt = _Notify.get(dev_index)
-    out = enqueue(cap, nt, lo, hi)
+    out = enqueue(cap, nt, lo, hi, mt)
     nt.wait()
     w = nt.words
     R = max(w[_ST_WORDS * f] for f in range(F))
     ovf = any(w[_ST_WORDS * f + 1] for f in range(F))
     dlo = min((_bits_to_float(w[_ST_WORDS * f + 3]) for f in range(F) if w[_ST_WORDS * f + 4]), default=0.0)
     dhi = max((_bits_to_float(w[_ST_WORDS * f + 4]) for f in range(F) if w[_ST_WORDS * f + 4]), default=0.0)
-    _Sizing.update(key, R, dlo, dhi)
+    _Sizing.update(key, R, dlo, dhi, max(w[_ST_WORDS * f + 2] for f in range(F)))
     if ovf:
-        cap, lo, hi = _Sizing.lookup(key, P)
-        out = enqueue(cap, nt, lo, hi)   # same inputs, capacity >= R: cannot overflow again
+        cap, lo, hi, mt = _Sizing.lookup(key, P)
+        out = enqueue(cap, nt, lo, hi, mt)   # same inputs, capacity >= R: cannot overflow again
         nt.wait()
         if any(w[_ST_WORDS * f + 1] for f in range(F)):
             raise _dgm_lib.DgmError("rasterizer: instance workspace overflow persisted after regrowth")
@@ -186,7 +187,7 @@ class _Workspace:
 
 def _raw_forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
                  projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered, R_cap, notify=None,
-                 lo=0.0, hi=0.0, out=None):
+                 lo=0.0, hi=0.0, out=None, max_tile=0):
     """One enqueue of dgr_forward.  Returns (color, radii, workspace)."""
     lib = _dgm_lib.lib()
     if means3D.ndim != 2 or means3D.shape[1] != 3:
@@ -206,7 +207,7 @@ def _raw_forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier
                          p(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), p(color), p(radii),
                          ws.geom, ws.gb, ws.binning, ws.bb, R_cap, ws.img, ws.ib, ws.status,
                          notify.host_ptr if notify else None, notify.event if notify else None, lo, hi,
-                         _dgm_lib.stream_ptr())
+                         int(max_tile), _dgm_lib.stream_ptr())
     _dgm_lib.check(rc, "dgr_forward")
     return color, radii, ws
 
@@ -235,10 +236,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         key = (dev_index, W, H)
         first = []
 
-        def run(R_cap, notify, lo, hi):
+        def run(R_cap, notify, lo, hi, mt):
             o = _raw_forward(bg, means3D, col, opac, sc, rot, rs.scale_modifier, cov, view, proj, rs.tanfovx,
                              rs.tanfovy, H, W, sh_, rs.sh_degree, campos, rs.prefiltered, R_cap, notify, lo, hi,
-                             first[0] if first else None)
+                             first[0] if first else None, mt)
             if not first:
                 first.append(o[:2])
             return o
@@ -383,7 +384,7 @@ class _RasterizeGaussiansBatch(torch.autograd.Function):
         p = _dgm_lib.ptr
         first = []
 
-        def run(R_cap, notify, lo, hi):
+        def run(R_cap, notify, lo, hi, mt):
             ws = _BatchWorkspace(F, P, W, H, R_cap, dev)
             if first:
                 color, radii = first[0]
@@ -396,7 +397,7 @@ class _RasterizeGaussiansBatch(torch.autograd.Function):
                                        p(cams), tx, ty, int(bool(rs0.prefiltered)), p(color), p(radii), ws.geom, ws.gs,
                                        ws.binning, ws.bs, R_cap, ws.img, ws.is_, ws.status,
                                        notify.host_ptr if notify else None, notify.event if notify else None, lo, hi,
-                                       _N_STREAMS, _dgm_lib.stream_ptr())
+                                       int(mt), _N_STREAMS, _dgm_lib.stream_ptr())
             _dgm_lib.check(rc, "dgr_forward_batch")
             return color, radii, ws
 
@@ -550,10 +551,10 @@ class _CCompat:
         key = (m3.device.index, int(image_width), int(image_height))
         first = []
 
-        def run(R_cap, notify, lo, hi):
+        def run(R_cap, notify, lo, hi, mt):
             o = _raw_forward(bg_, m3, col, op, sc, ro, scale_modifier, cov, view, proj, tan_fovx, tan_fovy,
                              int(image_height), int(image_width), sh_, degree, cam, prefiltered, R_cap, notify, lo, hi,
-                             first[0] if first else None)
+                             first[0] if first else None, mt)
             if not first:
                 first.append(o[:2])
             return o

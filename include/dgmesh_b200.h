@@ -96,7 +96,9 @@ int dgr_workspace_sizes(int P, int W, int H, int64_t R_cap,
  * depth_hint_lo < depth_hint_hi (view-depth range of an earlier, similar frame, from
  * status[DGR_ST_DEPTH_LO/HI]) lets preprocess build the (tile, depth-bucket) histogram
  * itself (one kernel less); the hint only affects bucket balance, never the result.
- * Pass 0, 0 when there is none. */
+ * Pass 0, 0 when there is none.  max_tile_hint (status[DGR_ST_MAX_TILE] of an earlier frame, 0 = unknown)
+ * selects the shared-memory capacity of the per-tile sort (object-filling scenes have lists of >6016 keys);
+ * like the depth hint it affects speed only. */
 int dgr_forward(int P, int D, int M,
                 const float* background, int W, int H,
                 const float* means3D, const float* shs, const float* colors_precomp,
@@ -109,7 +111,7 @@ int dgr_forward(int P, int D, int M,
                 void* binning_ws, size_t binning_bytes, int64_t R_cap,
                 void* img_ws, size_t img_bytes,
                 int32_t* status, int32_t* status_host, void* status_event,
-                float depth_hint_lo, float depth_hint_hi, void* stream);
+                float depth_hint_lo, float depth_hint_hi, int max_tile_hint, void* stream);
 
 /* Backward: same contract as Rasterizer::backward (rasterizer.h:54-84).  All
  * nine gradient outputs are fully written (zeros for culled Gaussians), the
@@ -173,7 +175,7 @@ int dgr_forward_batch(int F, int P, int D, int M,
                       void* binning_ws, size_t binning_stride, int64_t R_cap,
                       void* img_ws, size_t img_stride,
                       int32_t* status, int32_t* status_host, void* status_event,
-                      float depth_hint_lo, float depth_hint_hi, int n_streams, void* stream);
+                      float depth_hint_lo, float depth_hint_hi, int max_tile_hint, int n_streams, void* stream);
 
 int dgr_backward_batch(int F, int P, int D, int M,
                        const float* background, int W, int H,

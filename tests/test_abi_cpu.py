@@ -40,7 +40,7 @@ def test_workspace_query_and_argument_errors():
     assert lib.dgr_workspace_sizes(-1, 64, 48, 0, a, b, c) == -1          # DGM_E_BADARG
     # bad arguments are rejected on the host before anything touches a device
     rc = lib.dgr_forward(10, 0, 0, None, 64, 48, None, None, None, None, None, 1.0, None, None, None, None, None,
-                         1.0, 1.0, 0, None, None, None, 0, None, 0, 0, None, 0, None, None, None, 0.0, 0.0, None)
+                         1.0, 1.0, 0, None, None, None, 0, None, 0, 0, None, 0, None, None, None, 0.0, 0.0, 0, None)
     assert rc == -1 and b"null" in lib.dgm_last_error()
 
 

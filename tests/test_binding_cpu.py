@@ -101,7 +101,7 @@ def test_forward_backward_glue(stub, monkeypatch):
     assert [c[0] for c in stub.calls[n_before:]].count("dgr_forward") == 1
     last = [c for c in stub.calls if c[0] == "dgr_forward"][-1][1]
     assert last[26] >= dgr._grow(stub.R) and last[26] % 32 == 0
-    assert (last[32], last[33]) == (2.0, 6.0) and last[30] == 0x1000 and last[31] == 0x2000
+    assert (last[32], last[33]) == (2.0, 6.0) and last[30] == 0x1000 and last[31] == 0x2000 and last[34] == 0
     # a frame that does not fit (R grows 100x) is re-run transparently with a larger capacity: two enqueues,
     # the second into the SAME output tensors, no exception
     stub.R = 100 * stub.R + 1_000_000

@@ -181,6 +181,33 @@ def test_long_tile_list_global_sort_path():
 
 
 @needs_ref
+def test_object_shaped_scene_dense_tiles_all_sort_regimes():
+    """What DG-Mesh actually trains on: an object filling a fraction of the image -- thousands of instances per tile
+    inside a narrow depth range, i.e. depth buckets of hundreds to thousands of keys.  Exercises the warp-cooperative
+    and CTA-wide block sorts, the 24 576-key shared-memory variant (second call: chosen from the first call's
+    longest-tile hint) and the in-place global path; lists stay bit-exact."""
+    import diff_gaussian_rasterization as dgr
+    n = 40000
+    sc, cam = util.small_scene(n=n, W=160, H=128, seed=3, scale=0.02)
+    g = torch.Generator().manual_seed(5)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1)
+    sc["means3D"] = d * 0.35 + 0.004 * torch.randn(n, 3, generator=g)          # a thin shell around the origin
+    sc["means3D"][: n // 4] = 0.02 * torch.randn(n // 4, 3, generator=g)        # and a dense blob: one huge bucket
+    sc["opacities"] = sc["opacities"] * 0.05
+    sc, cam = _cuda(sc), _cam_cuda(cam)
+    bg = torch.zeros(3, device="cuda")
+    dpix = torch.randn(3, 128, 160, generator=torch.Generator().manual_seed(3)).cuda()
+    dgr._Sizing.hint.pop((torch.cuda.current_device(), 160, 128), None)
+    b = run_ref(sc, cam, bg, 3, False, False, dpix)
+    lens = (b["ranges"][:, 1] - b["ranges"][:, 0])
+    assert int(lens.max()) > 6016 and int((lens > 2048).sum()) >= 4, lens.max()
+    for attempt in ("no hint: default shared memory, long lists in global memory", "hinted: 24576-key shared memory"):
+        a = run_ours(sc, cam, bg, 3, False, False, dpix)
+        compare(a, b, label=f"object scene ({attempt})")
+    assert dgr._Sizing.hint[(torch.cuda.current_device(), 160, 128)][3] == int(lens.max())
+
+
+@needs_ref
 def test_full_size_config_c2_against_reference():
     """BASELINE.json configs[1]: 100k Gaussians, 800x800, SH degree 3."""
     import synth
@@ -291,7 +318,7 @@ def test_unmodified_loop_survives_growing_R_without_exception():
     sc = _cuda(sc)
     bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
     dgr._Sizing.hint.clear()
-    dgr._Sizing.hint[(torch.cuda.current_device(), 128, 96)] = [32, 0.0, 0.0]     # far too small to start with
+    dgr._Sizing.hint[(torch.cuda.current_device(), 128, 96)] = [32, 0.0, 0.0, 0]  # far too small to start with
     Rs, replays = [], 0
     for it, radius in enumerate((14.0, 8.0, 5.0, 3.0, 2.0, 5.0)):                # zooming in: R grows > 4x
         cam = _cam_cuda(synth.look_at_camera(azimuth_deg=30.0 * it, elevation_deg=10.0, radius=radius, width=128,

@@ -487,6 +487,9 @@ __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __rest
   if (tid == 0) s_end[0] = 0;
   __syncthreads();
   const uint32_t bstart = s_end[tid];
+  // which regimes does this tile need at all?  (spread-out scenes: insertion only -- skip the other two loops)
+  const int any_medium = __syncthreads_or(bend - bstart > BLOCK_SORT_MAX && bend - bstart <= WARP_SORT_MAX);
+  const int any_huge = __syncthreads_or(bend - bstart > WARP_SORT_MAX);
   if (bend - bstart <= BLOCK_SORT_MAX) {
     for (uint32_t i = bstart + 1; i < bend; ++i) {
       const unsigned long long key = a[i];
@@ -499,16 +502,18 @@ __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __rest
     }
   }
   __syncwarp();
-  // medium blocks: one warp each
-  for (uint32_t k = wid; k < DEPTH_BUCKETS; k += 8) {
-    const uint32_t s0 = s_end[k], len = s_end[k + 1] - s0;
-    if (len > BLOCK_SORT_MAX && len <= WARP_SORT_MAX) bitonic_sort_any<true>(a + s0, len, lane, 32);
+  if (any_medium) {  // medium blocks: one warp each
+    for (uint32_t k = wid; k < DEPTH_BUCKETS; k += 8) {
+      const uint32_t s0 = s_end[k], len = s_end[k + 1] - s0;
+      if (len > BLOCK_SORT_MAX && len <= WARP_SORT_MAX) bitonic_sort_any<true>(a + s0, len, lane, 32);
+    }
   }
-  __syncthreads();
-  // huge blocks: the whole CTA (uniform loop: every thread sees the same sizes)
-  for (uint32_t k = 0; k < DEPTH_BUCKETS; ++k) {
-    const uint32_t s0 = s_end[k], len = s_end[k + 1] - s0;
-    if (len > WARP_SORT_MAX) bitonic_sort_any<false>(a + s0, len, tid, 256);
+  if (any_huge) {  // huge blocks: the whole CTA (uniform loop: every thread sees the same sizes)
+    __syncthreads();
+    for (uint32_t k = 0; k < DEPTH_BUCKETS; ++k) {
+      const uint32_t s0 = s_end[k], len = s_end[k + 1] - s0;
+      if (len > WARP_SORT_MAX) bitonic_sort_any<false>(a + s0, len, tid, 256);
+    }
   }
   __syncthreads();
   const float* colors = colors_precomp ? colors_precomp : g.rgb;

@@ -195,11 +195,12 @@ def run_frames(dgr, synth, leaves, cams, dpix, bg, frame_ids, staged=None, delta
 
 class HostFeed:
     """e2e leg: every step the frames' cameras (35 floats each) and their ground-truth images (3xHxW
-    uint8, as a dataset stores them) are copied from PINNED HOST memory on a side stream, overlapped
-    with rendering; the pixel gradient is the L2-loss gradient (render - gt) formed on the device; the
-    step's result (a checksum of the accumulated parameter gradient) is copied back to the host every
-    step and read one step later (the usual lagged loss read of a training loop), the last one after
-    the final synchronise."""
+    uint8, as a dataset stores them) are copied from PINNED HOST memory on a side stream into one of TWO
+    device staging slots (the prefetch of a training loop's data loader: step i+1's upload runs while step i
+    renders; every copy is inside the timed region); the pixel gradient is the L2-loss gradient (render - gt)
+    formed on the device; the step's result (a checksum of the accumulated parameter gradient) is copied back
+    to the host every step and read one step later (the usual lagged loss read of a training loop), the last
+    one after the final synchronise."""
 
     def __init__(self, cams, frames, dev):
         self.frames = frames
@@ -209,14 +210,18 @@ class HostFeed:
                                              cams[k].camera_center.cpu().reshape(-1)]) for k in frames]).pin_memory()
         g = torch.Generator().manual_seed(7)
         self.h_gt = torch.randint(0, 256, (F, 3, HEIGHT, WIDTH), dtype=torch.uint8, generator=g).pin_memory()
-        self.d_cam = torch.empty_like(self.h_cam, device=dev)
-        self.d_gt = torch.empty_like(self.h_gt, device=dev)
-        self.views = [self.d_cam[i, 0:16].view(4, 4) for i in range(F)]
-        self.projs = [self.d_cam[i, 16:32].view(4, 4) for i in range(F)]
-        self.campos = [self.d_cam[i, 32:35] for i in range(F)]
-        self.ev_cam, self.ev_gt, self.consumed = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.slots = []
+        for _ in range(2):
+            d_cam = torch.empty_like(self.h_cam, device=dev)
+            sl = {"d_cam": d_cam, "d_gt": torch.empty_like(self.h_gt, device=dev),
+                  "views": [d_cam[i, 0:16].view(4, 4) for i in range(F)],
+                  "projs": [d_cam[i, 16:32].view(4, 4) for i in range(F)],
+                  "campos": [d_cam[i, 32:35] for i in range(F)],
+                  "ev_cam": torch.cuda.Event(), "ev_gt": torch.cuda.Event(), "consumed": torch.cuda.Event()}
+            sl["consumed"].record()
+            self.slots.append(sl)
+        self.cur = self.slots[0]
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.consumed.record()
         self.out_host = torch.zeros(2).pin_memory()
         self.out_ev = [None, None]
         self.n = 0
@@ -224,21 +229,25 @@ class HostFeed:
         self.h2d_bytes = self.h_cam.numel() * 4 + self.h_gt.numel()
 
     def upload(self):
-        self.copy_stream.wait_event(self.consumed)  # the previous step no longer reads the staging buffers
+        """Start this step's copies into the slot the step before last used; returns the slot."""
+        sl = self.cur = self.slots[self.n & 1]
+        self.copy_stream.wait_event(sl["consumed"])  # step n-2 no longer reads this slot
         with torch.cuda.stream(self.copy_stream):
-            self.d_cam.copy_(self.h_cam, non_blocking=True)
-            self.ev_cam.record(self.copy_stream)
-            self.d_gt.copy_(self.h_gt, non_blocking=True)
-            self.ev_gt.record(self.copy_stream)
+            sl["d_cam"].copy_(self.h_cam, non_blocking=True)
+            sl["ev_cam"].record(self.copy_stream)
+            sl["d_gt"].copy_(self.h_gt, non_blocking=True)
+            sl["ev_gt"].record(self.copy_stream)
+        return sl
 
     def pixel_grad(self, color, i=None):
         """d(L2 loss)/d(color) for the whole batch (i is None) or frame slot i."""
-        torch.cuda.current_stream().wait_event(self.ev_gt)
-        gt = self.d_gt if i is None else self.d_gt[i]
+        sl = self.cur
+        torch.cuda.current_stream().wait_event(sl["ev_gt"])
+        gt = sl["d_gt"] if i is None else sl["d_gt"][i]
         return torch.add(color.detach(), gt, alpha=-1.0 / 255.0)   # one kernel: uint8 -> float, scale, subtract
 
     def finish(self, result):
-        self.consumed.record()
+        self.cur["consumed"].record()
         slot = self.n & 1
         if self.out_ev[slot] is not None:      # the result of step n-2 has long arrived: read it
             self.out_ev[slot].synchronize()
@@ -495,15 +504,16 @@ def main():
     # ---- e2e leg: host buffers, copies inside the timed region
     feed = HostFeed(cams, my_frames, dev)
     if ours:
-        feed_settings = batch_settings(dgr, cams, bg, my_frames, feed.views, feed.projs, feed.campos)
+        for sl in feed.slots:
+            sl["settings"] = batch_settings(dgr, cams, bg, my_frames, sl["views"], sl["projs"], sl["campos"])
 
     def step_e2e():
-        feed.upload()
+        sl = feed.upload()
         gflat.zero_()
         if ours:
-            run_batch(dgr, leaves, feed_settings, feed.pixel_grad, wait_fwd=feed.ev_cam, deltas=my_deltas)
+            run_batch(dgr, leaves, sl["settings"], feed.pixel_grad, wait_fwd=sl["ev_cam"], deltas=my_deltas)
         else:
-            staged = {k: (feed.ev_cam, feed.views[i], feed.projs[i], feed.campos[i],
+            staged = {k: (sl["ev_cam"], sl["views"][i], sl["projs"][i], sl["campos"][i],
                           (lambda c, i=i: feed.pixel_grad(c, i))) for i, k in enumerate(my_frames)}
             run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged, deltas=deltas_all)
         if world > 1:
@@ -523,9 +533,9 @@ def main():
         feed1 = HostFeed(cams, my_frames, dev)
 
         def step_single_e2e():
-            feed1.upload()
+            sl = feed1.upload()
             gflat.zero_()
-            staged = {k: (feed1.ev_cam, feed1.views[i], feed1.projs[i], feed1.campos[i],
+            staged = {k: (sl["ev_cam"], sl["views"][i], sl["projs"][i], sl["campos"][i],
                           (lambda c, i=i: feed1.pixel_grad(c, i))) for i, k in enumerate(my_frames)}
             run_frames(dgr, synth, leaves, cams, dpix, bg, my_frames, staged=staged, deltas=deltas_all)
             if world > 1:

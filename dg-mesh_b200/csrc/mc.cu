@@ -7,18 +7,19 @@
 // vertex / face ORDER cannot be reproduced, only the surface.  Case tables are derived by
 // tools/gen_mc_tables.py (watertight by construction).
 //
-// Warp-cooperative sweep (z fastest: a warp owns a strip of 32 consecutive nodes (i, j, k0..k0+31) and
-// loads the four phi rows (i|i+1, j|j+1) of its strip once, coalesced; the k+1 neighbours come from the
-// same rows), hierarchical counting instead of a per-node scan:
-//   count   per CTA (8 strips = 256 nodes): ONE packed (vertices | triangles << 32) total      [reads phi once]
-//   scan    cub::DeviceScan over the ~n/256 CTA totals (library primitive), totals -> device + mapped host
-//   emit    only CTAs that own something re-read their strips (a few % of the grid): intra-CTA prefix sums
-//           give every vertex its index; vertices are written, the owner table vid[node] = first vertex |
+// Warp-per-brick sweep.  A BRICK is 8 (j) x 32 (k) nodes of one i-plane; a warp owns one brick: lane = k, and
+// every lane loads the 9 rows (j .. j+8) of planes i and i+1 at its k -- 18 independent, fully coalesced loads
+// in flight per lane, 2.25 loads per node instead of 8 -- the k+1 neighbours come from the next lane by shuffle
+// (lane 31 fetches its own).  No shared memory, no CTA barrier.  Hierarchical counting instead of a per-node scan:
+//   count   per brick: ONE packed (vertices | triangles << 32) total                              [reads phi once]
+//   scan    cub::DeviceScan over the n/256 brick totals (library primitive), totals -> device + mapped host
+//   emit    only warps whose brick owns something re-read it (a few % of the grid): a warp prefix sum gives
+//           every vertex its index; vertices are written, the owner table vid[node] = first vertex |
 //           edge mask << 29 is filled SPARSELY (only nodes that own vertices are ever looked up), faces are
 //           written as encoded owner references (node * 3 + axis), and vsrc[v] remembers each vertex's edge
 //   resolve 3F threads turn the owner references into vertex indices through vid[]
 // Backward: one thread per VERTEX (vsrc), d verts / d phi through t = (iso - phi0) / (phi1 - phi0).
-// Scratch traffic is ~8 B per CTA instead of 26 B per node: the sweep is bound by reading phi once
+// Scratch traffic is 8 B per brick instead of 26 B per node: the sweep is bound by reading phi once
 // (4 G^3 bytes) rather than by its own bookkeeping.
 #include <cub/device/device_scan.cuh>
 
@@ -32,85 +33,101 @@ __constant__ unsigned char c_ntri[256];
 __constant__ signed char c_tri[256][MC_MAX_TRI * 3];
 __constant__ unsigned char c_edge_lo[12];
 
-#define MC_STRIPS 8  // warps (strips of 32 nodes) per CTA
+#define MC_WARPS 8  // bricks (warps) per CTA
+#define MC_BJ 8     // j-rows per brick
 
 struct McGeom {
-  int G, spr;        // grid size, strips per (i, j) row = ceil(G / 32)
-  size_t nstrips;    // G * G * spr
+  int G, spr, njb;   // grid size, k-chunks per row = ceil(G / 32), j-blocks per plane = ceil(G / MC_BJ)
+  size_t nbricks;    // G * njb * spr
 };
 __host__ __device__ inline McGeom mc_geom(int G) {
   McGeom g;
   g.G = G;
   g.spr = (G + 31) / 32;
-  g.nstrips = (size_t)G * G * g.spr;
+  g.njb = (G + MC_BJ - 1) / MC_BJ;
+  g.nbricks = (size_t)G * g.njb * g.spr;
   return g;
 }
-size_t mc_num_blocks(int G) { return (mc_geom(G).nstrips + MC_STRIPS - 1) / MC_STRIPS; }
+size_t mc_num_blocks(int G) { return mc_geom(G).nbricks; }
 
-// what one lane knows about its node after the strip loads
-struct McNode {
-  bool valid;
-  int i, j, k;
-  size_t id;
-  unsigned mask, cs;  // owned-edge mask (bit a: the edge towards +axis a carries a vertex), cell case
-  float p0, p1[3];    // phi at the node and at its +x / +y / +z neighbours
+// one lane's view of its brick: phi at (i + p, j0 + r, k) and at k + 1, r = 0..MC_BJ (out of range = 0)
+struct McBrick {
+  int i, j0, k;
+  bool xi, zk, kin;
+  float a[2][MC_BJ + 1], z[2][MC_BJ + 1];
 };
 
-__device__ __forceinline__ McNode mc_load(const McGeom& g, size_t strip, unsigned lane, const float* __restrict__ phi,
-                                          float iso) {
-  McNode n;
+__device__ __forceinline__ void mc_load_brick(const McGeom& g, size_t brick, unsigned lane,
+                                              const float* __restrict__ phi, McBrick& B) {
   const int G = g.G;
-  n.valid = strip < g.nstrips;
-  const size_t row = n.valid ? strip / g.spr : 0;
-  n.k = (int)((n.valid ? strip % g.spr : 0) * 32 + lane);
-  n.j = (int)(row % G);
-  n.i = (int)(row / G);
-  n.valid = n.valid && n.k < G;
-  n.id = ((size_t)n.i * G + n.j) * G + n.k;
-  n.mask = n.cs = 0;
-  n.p0 = n.p1[0] = n.p1[1] = n.p1[2] = 0.f;
-  if (!n.valid) return n;
-  const bool xi = n.i + 1 < G, yj = n.j + 1 < G, zk = n.k + 1 < G;
-  const float* r00 = phi + n.id;
-  const size_t sx = (size_t)G * G, sy = G;
-  float v[8];
-  v[0] = r00[0];
-  v[1] = xi ? r00[sx] : 0.f;
-  v[2] = yj ? r00[sy] : 0.f;
-  v[3] = (xi && yj) ? r00[sx + sy] : 0.f;
-  v[4] = zk ? r00[1] : 0.f;
-  v[5] = (xi && zk) ? r00[sx + 1] : 0.f;
-  v[6] = (yj && zk) ? r00[sy + 1] : 0.f;
-  v[7] = (xi && yj && zk) ? r00[sx + sy + 1] : 0.f;
-  n.p0 = v[0], n.p1[0] = v[1], n.p1[1] = v[2], n.p1[2] = v[4];
-  const bool s0 = v[0] < iso;
-  if (xi && ((v[1] < iso) != s0)) n.mask |= 1;
-  if (yj && ((v[2] < iso) != s0)) n.mask |= 2;
-  if (zk && ((v[4] < iso) != s0)) n.mask |= 4;
-  if (xi && yj && zk) {
+  const int kc = (int)(brick % g.spr);
+  const size_t t = brick / g.spr;
+  B.j0 = (int)(t % g.njb) * MC_BJ;
+  B.i = (int)(t / g.njb);
+  B.k = kc * 32 + (int)lane;
+  B.kin = B.k < G;
+  B.xi = B.i + 1 < G;
+  B.zk = B.k + 1 < G;
+  const float* base = phi + ((size_t)B.i * G + B.j0) * G + B.k;
+  const size_t sx = (size_t)G * G;
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (v[c] < iso) n.cs |= 1u << c;  // corner c = (i + (c & 1), j + ((c >> 1) & 1), k + (c >> 2))
+  for (int r = 0; r <= MC_BJ; ++r) {
+    const bool jin = B.j0 + r < G;
+    B.a[0][r] = (jin && B.kin) ? base[(size_t)r * G] : 0.f;
+    B.a[1][r] = (jin && B.kin && B.xi) ? base[sx + (size_t)r * G] : 0.f;
   }
-  return n;
+  // the k + 1 column: lanes 0..30 take their neighbour's value, lane 31 reads the next chunk's first element
+#pragma unroll
+  for (int r = 0; r <= MC_BJ; ++r) {
+    const bool jin = B.j0 + r < G;
+    float e0 = 0.f, e1 = 0.f;
+    if (lane == 31 && jin && B.zk) {
+      e0 = base[(size_t)r * G + 1];
+      if (B.xi) e1 = base[sx + (size_t)r * G + 1];
+    }
+    const float n0 = __shfl_down_sync(0xffffffffu, B.a[0][r], 1), n1 = __shfl_down_sync(0xffffffffu, B.a[1][r], 1);
+    B.z[0][r] = lane == 31 ? e0 : n0;
+    B.z[1][r] = lane == 31 ? e1 : n1;
+  }
 }
 
-__global__ void __launch_bounds__(32 * MC_STRIPS) mc_count_kernel(McGeom g, const float* __restrict__ phi, float iso,
-                                                                  unsigned long long* __restrict__ blk_counts) {
-  __shared__ unsigned s_part[MC_STRIPS];
+// node r of the lane: owned-edge mask (bit a: the edge towards +axis a carries a vertex) and cell case
+__device__ __forceinline__ void mc_classify(const McGeom& g, const McBrick& B, int r, float iso, unsigned& mask,
+                                            unsigned& cs) {
+  mask = cs = 0;
+  const int j = B.j0 + r;
+  if (!B.kin || j >= g.G) return;
+  const bool yj = j + 1 < g.G;
+  const float v0 = B.a[0][r], v1 = B.a[1][r], v2 = B.a[0][r + 1], v3 = B.a[1][r + 1];
+  const float v4 = B.z[0][r], v5 = B.z[1][r], v6 = B.z[0][r + 1], v7 = B.z[1][r + 1];
+  const bool s0 = v0 < iso;
+  if (B.xi && ((v1 < iso) != s0)) mask |= 1;
+  if (yj && ((v2 < iso) != s0)) mask |= 2;
+  if (B.zk && ((v4 < iso) != s0)) mask |= 4;
+  if (B.xi && yj && B.zk) {  // corner c = (i + (c & 1), j + ((c >> 1) & 1), k + (c >> 2))
+    cs = (unsigned)s0 | ((unsigned)(v1 < iso) << 1) | ((unsigned)(v2 < iso) << 2) | ((unsigned)(v3 < iso) << 3) |
+         ((unsigned)(v4 < iso) << 4) | ((unsigned)(v5 < iso) << 5) | ((unsigned)(v6 < iso) << 6) |
+         ((unsigned)(v7 < iso) << 7);
+  }
+}
+
+__global__ void __launch_bounds__(32 * MC_WARPS) mc_count_kernel(McGeom g, const float* __restrict__ phi, float iso,
+                                                                 unsigned long long* __restrict__ blk_counts) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const McNode n = mc_load(g, (size_t)blockIdx.x * MC_STRIPS + wid, lane, phi, iso);
-  unsigned c = __popc(n.mask) | ((unsigned)c_ntri[n.cs] << 16);  // <= 96 / 160 per warp: 16 bits each suffice
+  const size_t brick = (size_t)blockIdx.x * MC_WARPS + wid;
+  if (brick >= g.nbricks) return;
+  McBrick B;
+  mc_load_brick(g, brick, lane, phi, B);
+  unsigned c = 0;  // vertices | triangles << 16: <= 768 / 1280 per brick
+#pragma unroll
+  for (int r = 0; r < MC_BJ; ++r) {
+    unsigned mask, cs;
+    mc_classify(g, B, r, iso, mask, cs);
+    c += __popc(mask) | ((unsigned)c_ntri[cs] << 16);
+  }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if (lane == 0) s_part[wid] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long nv = 0, nt = 0;
-#pragma unroll
-    for (int w = 0; w < MC_STRIPS; ++w) nv += s_part[w] & 0xffffu, nt += s_part[w] >> 16;
-    blk_counts[blockIdx.x] = nv | (nt << 32);
-  }
+  if (lane == 0) blk_counts[brick] = (unsigned long long)(c & 0xffffu) | ((unsigned long long)(c >> 16) << 32);
 }
 
 __global__ void mc_totals_kernel(size_t nb, const unsigned long long* __restrict__ counts,
@@ -126,61 +143,74 @@ __global__ void mc_totals_kernel(size_t nb, const unsigned long long* __restrict
   }
 }
 
-__global__ void __launch_bounds__(32 * MC_STRIPS) mc_emit_kernel(
+__global__ void __launch_bounds__(32 * MC_WARPS) mc_emit_kernel(
     McGeom g, const float* __restrict__ phi, float iso, const unsigned long long* __restrict__ blk_counts,
     const unsigned long long* __restrict__ blk_offsets, uint32_t* __restrict__ vid, uint32_t* __restrict__ vsrc,
     float* __restrict__ verts, long long V_cap, int32_t* __restrict__ faces, long long F_cap) {
-  __shared__ unsigned s_part[MC_STRIPS];
-  if (blk_counts[blockIdx.x] == 0) return;  // nothing owned here (the vast majority of CTAs)
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const McNode n = mc_load(g, (size_t)blockIdx.x * MC_STRIPS + wid, lane, phi, iso);
-  const unsigned mine = __popc(n.mask) | ((unsigned)c_ntri[n.cs] << 16);
-  unsigned inc = mine;  // inclusive prefix inside the warp
+  const size_t brick = (size_t)blockIdx.x * MC_WARPS + wid;
+  if (brick >= g.nbricks || blk_counts[brick] == 0) return;  // nothing owned here (the vast majority of bricks)
+  McBrick B;
+  mc_load_brick(g, brick, lane, phi, B);
+  unsigned masks = 0, css[MC_BJ];  // 3 bits of mask per node, packed
+  unsigned mine = 0;
+#pragma unroll
+  for (int r = 0; r < MC_BJ; ++r) {
+    unsigned mask;
+    mc_classify(g, B, r, iso, mask, css[r]);
+    masks |= mask << (3 * r);
+    mine += __popc(mask) | ((unsigned)c_ntri[css[r]] << 16);
+  }
+  unsigned inc = mine;  // inclusive prefix over the lanes (order inside the brick: lane-major, then r)
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= (unsigned)o) inc += up;
   }
-  if (lane == 31) s_part[wid] = inc;
-  __syncthreads();
-  unsigned before = 0;
-  for (unsigned w = 0; w < wid; ++w) before += s_part[w];
-  const unsigned excl = before + inc - mine;
-  const unsigned long long base = blk_offsets[blockIdx.x];
-  const unsigned long long v0 = (base & 0xffffffffull) + (excl & 0xffffu);
-  const unsigned long long f0 = (base >> 32) + (excl >> 16);
+  if (mine == 0) return;
+  const unsigned excl = inc - mine;
+  const unsigned long long base = blk_offsets[brick];
+  unsigned long long v = (base & 0xffffffffull) + (excl & 0xffffu);
+  unsigned long long f = (base >> 32) + (excl >> 16);
   const int G = g.G;
-  if (n.mask) {
-    vid[n.id] = (uint32_t)v0 | (n.mask << 29);
-    const float gm1 = (float)(G - 1);
-    const float basep[3] = {(float)n.i, (float)n.j, (float)n.k};
-    unsigned long long v = v0;
+  const float gm1 = (float)(G - 1);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (n.mask & (1u << a)) {
-        if ((long long)v < V_cap) {
-          const float t = (iso - n.p0) / (n.p1[a] - n.p0);
-          float pos[3] = {basep[0], basep[1], basep[2]};
-          pos[a] += t;
-          verts[3 * v + 0] = pos[0] / gm1;  // IEEE division: identical to the numpy restatement
-          verts[3 * v + 1] = pos[1] / gm1;
-          verts[3 * v + 2] = pos[2] / gm1;
-          vsrc[v] = (uint32_t)(n.id * 3 + a);
+  for (int r = 0; r < MC_BJ; ++r) {
+    const unsigned mask = (masks >> (3 * r)) & 7u, cs = css[r];
+    if (mask == 0 && cs == 0) continue;
+    const int j = B.j0 + r;
+    const size_t id = ((size_t)B.i * G + j) * G + B.k;
+    if (mask) {
+      vid[id] = (uint32_t)v | (mask << 29);
+      const float p0 = B.a[0][r];
+      const float p1[3] = {B.a[1][r], B.a[0][r + 1], B.z[0][r]};
+      const float basep[3] = {(float)B.i, (float)j, (float)B.k};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (mask & (1u << a)) {
+          if ((long long)v < V_cap) {
+            const float t = (iso - p0) / (p1[a] - p0);
+            float pos[3] = {basep[0], basep[1], basep[2]};
+            pos[a] += t;
+            verts[3 * v + 0] = pos[0] / gm1;  // IEEE division: identical to the numpy restatement
+            verts[3 * v + 1] = pos[1] / gm1;
+            verts[3 * v + 2] = pos[2] / gm1;
+            vsrc[v] = (uint32_t)(id * 3 + a);
+          }
+          ++v;
         }
-        ++v;
       }
     }
-  }
-  const int nt = c_ntri[n.cs];
-  unsigned long long f = f0;
-  for (int t = 0; t < nt; ++t, ++f) {
-    if ((long long)f >= F_cap) break;
+    const int nt = c_ntri[cs];
+    for (int t = 0; t < nt; ++t, ++f) {
+      if ((long long)f >= F_cap) break;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int e = c_tri[n.cs][3 * t + q];
-      const int c = c_edge_lo[e], axis = e >> 2;
-      const size_t owner = ((size_t)(n.i + (c & 1)) * G + (n.j + ((c >> 1) & 1))) * G + (n.k + (c >> 2));
-      faces[3 * f + q] = (int32_t)(owner * 3 + axis);  // resolved by mc_resolve_kernel
+      for (int q = 0; q < 3; ++q) {
+        const int e = c_tri[cs][3 * t + q];
+        const int c = c_edge_lo[e], axis = e >> 2;
+        const size_t owner = ((size_t)(B.i + (c & 1)) * G + (j + ((c >> 1) & 1))) * G + (B.k + (c >> 2));
+        faces[3 * f + q] = (int32_t)(owner * 3 + axis);  // resolved by mc_resolve_kernel
+      }
     }
   }
 }
@@ -255,7 +285,7 @@ cudaError_t launch_mc_count(int G, const float* phi, float iso, void* ws, int32_
   McWS w = McWS::from((char*)ws, G);
   const McGeom g = mc_geom(G);
   const size_t nb = mc_num_blocks(G);
-  mc_count_kernel<<<(unsigned)nb, 32 * MC_STRIPS, 0, s>>>(g, phi, iso, w.blk_counts);
+  mc_count_kernel<<<(unsigned)((nb + MC_WARPS - 1) / MC_WARPS), 32 * MC_WARPS, 0, s>>>(g, phi, iso, w.blk_counts);
   size_t tb = w.cub_bytes;
   cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, w.blk_counts, w.blk_offsets, (int)nb, s);
   mc_totals_kernel<<<1, 1, 0, s>>>(nb, w.blk_counts, w.blk_offsets, w.totals, nullptr);
@@ -271,8 +301,8 @@ cudaError_t launch_mc_emit(int G, const float* phi, float iso, void* ws, float* 
   const size_t nb = mc_num_blocks(G);
   const size_t n = (size_t)G * G * G;
   if (V_cap > (long long)n) V_cap = (long long)n;
-  mc_emit_kernel<<<(unsigned)nb, 32 * MC_STRIPS, 0, s>>>(g, phi, iso, w.blk_counts, w.blk_offsets, w.vid, w.vsrc, verts,
-                                                         V_cap, faces, F_cap);
+  mc_emit_kernel<<<(unsigned)((nb + MC_WARPS - 1) / MC_WARPS), 32 * MC_WARPS, 0, s>>>(
+      g, phi, iso, w.blk_counts, w.blk_offsets, w.vid, w.vsrc, verts, V_cap, faces, F_cap);
   if (F_cap > 0)
     mc_resolve_kernel<<<(unsigned)((3 * F_cap + 255) / 256), 256, 0, s>>>(w.totals, F_cap, w.vid, faces);
   return cudaGetLastError();

@@ -6,7 +6,7 @@
 
 namespace dgm {
 struct McWS {
-  unsigned long long *blk_counts, *blk_offsets;  // per CTA of 256 nodes: (vertices | triangles << 32), exclusive scan
+  unsigned long long *blk_counts, *blk_offsets;  // per brick of 8 x 32 nodes: (vertices | triangles << 32), exclusive scan
   int32_t* totals;                                // device copy of {V, F} for the resolve pass
   uint32_t* vid;                                  // [n] sparse: first vertex index | owned-edge mask << 29
   uint32_t* vsrc;                                 // [V] node * 3 + axis of every vertex (backward pass)

@@ -407,22 +407,26 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, GeomWS g, const uin
 }
 
 // ======================================================= tile sort+pack ====
-// One CTA per tile: the segment is already partitioned into DEPTH_BUCKETS depth-ordered blocks (scatter
-// left each block's END in hist); sort every block by (depth bits, gaussian id) -- which is exactly the
-// order the reference's stable sort on (tile | depth) yields -- then write point_list and the packed blend
-// records.  Block sizes vary by orders of magnitude between scenes: a spread-out scene (C2) has ~1 key per
-// block, an object that fills a seventh of the image (what DG-Mesh trains on) has thousands of keys per
-// tile in a few dozen blocks.  Three regimes, chosen per BLOCK, not per tile:
-//   <= 48 keys      insertion sort by the block's own thread
-//   <= 2048 keys    warp-cooperative bitonic network (normalised: all comparators ascending, so virtual
-//                   +inf padding never moves and any length works); the 8 warps take such blocks round-robin
-//   larger          the whole CTA sorts the block
-// Keys are staged in dynamic shared memory when the segment fits (capacity chosen by the host from the
-// previous frame's longest tile, status word 2), else sorted in place in global memory (L2-resident).
-#define SORT_SMEM_KEYS 6016       // default capacity: 47 KB
-#define SORT_SMEM_KEYS_BIG 24576  // dense scenes: 192 KB, one CTA per SM
-#define BLOCK_SORT_MAX 48         // longest block one thread sorts by insertion
-#define WARP_SORT_MAX 2048        // longest block one warp sorts
+// One CTA per tile (longest lists first): the segment is already partitioned into DEPTH_BUCKETS depth-ordered
+// blocks (scatter left each block's END in hist); sort every block by (depth bits, gaussian id) -- which is
+// exactly the order the reference's stable sort on (tile | depth) yields -- then write point_list and the packed
+// blend records.  Block sizes vary by orders of magnitude between scenes: a spread-out scene (C2) has ~1 key per
+// block, an object that fills a seventh of the image (what DG-Mesh trains on) has thousands of keys per tile in
+// a few dozen blocks.
+//   * A tile is processed in RUNS of consecutive blocks that fit the 24 KB key stage (eight CTAs per SM whatever
+//     the scene): load the run, sort its blocks, pack its records, next run.  A tile of any length is handled at
+//     full occupancy; only a single block longer than the stage is sorted in place in global memory.
+//   * Four sort regimes, chosen per BLOCK:
+//       <= 8 keys      insertion sort by the block's own thread
+//       <= 32 keys     one warp, keys in registers, bitonic network over shuffles
+//       <= 2048 keys   one warp, bitonic network in shared memory (normalised: all comparators ascending, so
+//                      virtual +inf padding never moves and any length works)
+//       larger         the whole CTA
+//     Thread (warp w, lane l) owns block 8 l + w, so depth-adjacent (similarly full) blocks land in different
+//     warps; a warp finds the blocks it has to sort cooperatively with one ballot over its own lanes.
+#define SORT_STAGE_KEYS 3072  // 24 KB
+#define INSERT_SORT_MAX 8     // longest block one thread sorts by insertion
+#define WARP_SORT_MAX 2048    // longest block one warp sorts
 
 __device__ __forceinline__ void cmpswap(unsigned long long* a, uint32_t lo, uint32_t hi, uint32_t n) {
   if (hi < n) {
@@ -459,82 +463,137 @@ __device__ __forceinline__ void bitonic_sort_any(unsigned long long* a, uint32_t
   }
 }
 
+// a[0..n), n <= 32: one key per lane, bitonic network over shuffles (padding = all ones sorts last)
+__device__ __forceinline__ void warp_sort32(unsigned long long* a, uint32_t n, uint32_t lane) {
+  unsigned long long x = lane < n ? a[lane] : ~0ull;
+#pragma unroll
+  for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
+      const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
+      x = take_min ? (x < y ? x : y) : (x < y ? y : x);
+    }
+  }
+  if (lane < n) a[lane] = x;
+}
+
+struct PackRec {
+  uint32_t id;
+  float4 geo, attr0, attr1;
+};
+__device__ __forceinline__ PackRec pack_record(unsigned long long k, const GeomWS& g, const float* __restrict__ colors) {
+  PackRec r;
+  r.id = (uint32_t)(k & 0xffffffffull);
+  const float2 xy = g.means2D[r.id];
+  const float4 co = g.conic_opacity[r.id];
+  const float c0 = colors[3 * r.id], c1 = colors[3 * r.id + 1], c2 = colors[3 * r.id + 2];
+  // 2*(ln(255 o) + margin): the level of q = -2 power below which alpha >= 1/255 is possible
+  // (see cull_keep); -1 when the opacity alone rules it out, +inf for a degenerate conic
+  float q2tau;
+  const float tau = __logf(255.0f * co.w) + 0.02f;
+  const float det = co.x * co.z - co.y * co.y;
+  if (!(tau > 0.0f)) q2tau = -1.0f;
+  else if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f) || !isfinite(det) || !isfinite(tau)) q2tau = 3.0e38f;
+  else q2tau = 2.0f * tau;
+  r.geo = make_float4(xy.x, xy.y, q2tau, 0.0f);
+  r.attr0 = co;
+  r.attr1 = make_float4(c0, c1, c2, __uint_as_float(r.id));
+  return r;
+}
+__device__ __forceinline__ void store_record(const BinWS& b, size_t o, const PackRec& r) {
+  b.point_list[o] = r.id;
+  b.inst_geo[o] = r.geo;
+  b.inst_attr[2 * o] = r.attr0;
+  b.inst_attr[2 * o + 1] = r.attr1;
+}
+// records of sorted keys a[0..cnt) -> instance slots first + i; two keys per thread in flight
+__device__ __forceinline__ void pack_run(const unsigned long long* a, uint32_t cnt, size_t first, const GeomWS& g,
+                                         const float* __restrict__ colors, const BinWS& b, uint32_t tid) {
+  uint32_t i = tid;
+  for (; i + 256 < cnt; i += 512) {
+    const PackRec r0 = pack_record(a[i], g, colors), r1 = pack_record(a[i + 256], g, colors);
+    store_record(b, first + i, r0);
+    store_record(b, first + i + 256, r1);
+  }
+  if (i < cnt) store_record(b, first + i, pack_record(a[i], g, colors));
+}
+
 __global__ void __launch_bounds__(256) tile_sort_pack_kernel(const uint2* __restrict__ ranges,
+                                                             const uint32_t* __restrict__ tile_order,
                                                              unsigned long long* __restrict__ keys,
                                                              const uint32_t* __restrict__ hist, GeomWS g,
                                                              const float* __restrict__ colors_precomp, BinWS b,
-                                                             const int32_t* __restrict__ status, uint32_t smem_keys) {
-  extern __shared__ __align__(16) unsigned long long s_keys[];
+                                                             const int32_t* __restrict__ status) {
+  __shared__ __align__(16) unsigned long long s_keys[SORT_STAGE_KEYS];
   __shared__ uint32_t s_end[DEPTH_BUCKETS + 1];  // s_end[k] = start of block k, s_end[k + 1] = its end
   pdl_wait();
   pdl_launch();
   if (status[1]) return;
-  const uint2 range = ranges[blockIdx.x];
+  const uint32_t tile = tile_order[blockIdx.x];  // longest lists first (shorter tail in dense scenes)
+  const uint2 range = ranges[tile];
   const uint32_t n = range.y - range.x;
   if (n == 0) return;
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t mine = lane * 8 + wid;  // the block this thread owns
   unsigned long long* seg = keys + range.x;
-  unsigned long long* a;
-  if (n <= smem_keys) {
-    for (uint32_t i = tid; i < n; i += 256) s_keys[i] = seg[i];
-    a = s_keys;
-  } else {
-    a = seg;  // rare: work on the segment in place in global memory (L2-resident)
-  }
-  // block tid of this tile: [bstart, bend) relative to the segment (scatter left the block END in hist)
-  const uint32_t bend = hist[(size_t)blockIdx.x * DEPTH_BUCKETS + tid];
-  s_end[tid + 1] = bend;
+  const float* colors = colors_precomp ? colors_precomp : g.rgb;
+  // (scatter left the block END, relative to the segment, in hist)
+  s_end[mine + 1] = hist[(size_t)tile * DEPTH_BUCKETS + mine];
   if (tid == 0) s_end[0] = 0;
   __syncthreads();
-  const uint32_t bstart = s_end[tid];
-  // which regimes does this tile need at all?  (spread-out scenes: insertion only -- skip the other two loops)
-  const int any_medium = __syncthreads_or(bend - bstart > BLOCK_SORT_MAX && bend - bstart <= WARP_SORT_MAX);
-  const int any_huge = __syncthreads_or(bend - bstart > WARP_SORT_MAX);
-  if (bend - bstart <= BLOCK_SORT_MAX) {
-    for (uint32_t i = bstart + 1; i < bend; ++i) {
-      const unsigned long long key = a[i];
-      uint32_t j = i;
-      while (j > bstart && a[j - 1] > key) {
-        a[j] = a[j - 1];
-        --j;
+  const uint32_t bstart = s_end[mine], blen = s_end[mine + 1] - bstart;
+
+  uint32_t k0 = 0;
+  while (k0 < DEPTH_BUCKETS) {
+    const uint32_t start = s_end[k0];
+    if (start == n) break;  // only empty blocks left
+    // blocks [k0, k1) fit the stage (s_end is monotone: the predicate holds on a prefix of [k0, 256))
+    const uint32_t fit = __syncthreads_count(tid >= k0 && s_end[tid + 1] - start <= SORT_STAGE_KEYS);
+    if (fit == 0) {  // block k0 alone is longer than the stage: sort it where it lies (rare)
+      const uint32_t len = s_end[k0 + 1] - start;
+      bitonic_sort_any<false>(seg + start, len, tid, 256);
+      pack_run(seg + start, len, (size_t)range.x + start, g, colors, b, tid);
+      k0 += 1;
+      continue;
+    }
+    const uint32_t k1 = k0 + fit, cnt = s_end[k1] - start;
+    for (uint32_t i = tid; i < cnt; i += 256) s_keys[i] = seg[start + i];
+    const bool in_run = mine >= k0 && mine < k1;
+    const uint32_t len = in_run ? blen : 0;
+    const int any_huge = __syncthreads_or(len > WARP_SORT_MAX);  // also: the stage is loaded
+    unsigned long long* a = s_keys + (bstart - start);           // this thread's block (valid when in_run)
+    if (len > 1 && len <= INSERT_SORT_MAX) {
+      for (uint32_t i = 1; i < len; ++i) {
+        const unsigned long long key = a[i];
+        uint32_t j = i;
+        while (j > 0 && a[j - 1] > key) {
+          a[j] = a[j - 1];
+          --j;
+        }
+        a[j] = key;
       }
-      a[j] = key;
     }
-  }
-  __syncwarp();
-  if (any_medium) {  // medium blocks: one warp each
-    for (uint32_t k = wid; k < DEPTH_BUCKETS; k += 8) {
-      const uint32_t s0 = s_end[k], len = s_end[k + 1] - s0;
-      if (len > BLOCK_SORT_MAX && len <= WARP_SORT_MAX) bitonic_sort_any<true>(a + s0, len, lane, 32);
+    // blocks of this warp's lanes that need the whole warp
+    uint32_t coop = __ballot_sync(0xffffffffu, len > INSERT_SORT_MAX && len <= WARP_SORT_MAX);
+    while (coop) {
+      const uint32_t l = __ffs(coop) - 1;
+      coop &= coop - 1;
+      const uint32_t s0 = __shfl_sync(0xffffffffu, bstart, l) - start, ln = __shfl_sync(0xffffffffu, len, l);
+      if (ln <= 32) warp_sort32(s_keys + s0, ln, lane);
+      else bitonic_sort_any<true>(s_keys + s0, ln, lane, 32);
     }
-  }
-  if (any_huge) {  // huge blocks: the whole CTA (uniform loop: every thread sees the same sizes)
+    if (any_huge) {  // uniform loop: every thread sees the same sizes
+      __syncthreads();
+      for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t s0 = s_end[k], ln = s_end[k + 1] - s0;
+        if (ln > WARP_SORT_MAX) bitonic_sort_any<false>(s_keys + (s0 - start), ln, tid, 256);
+      }
+    }
     __syncthreads();
-    for (uint32_t k = 0; k < DEPTH_BUCKETS; ++k) {
-      const uint32_t s0 = s_end[k], len = s_end[k + 1] - s0;
-      if (len > WARP_SORT_MAX) bitonic_sort_any<false>(a + s0, len, tid, 256);
-    }
-  }
-  __syncthreads();
-  const float* colors = colors_precomp ? colors_precomp : g.rgb;
-  for (uint32_t i = tid; i < n; i += 256) {
-    const unsigned long long k = a[i];
-    const uint32_t id = (uint32_t)(k & 0xffffffffull);
-    const float2 xy = g.means2D[id];
-    const float4 co = g.conic_opacity[id];
-    // 2*(ln(255 o) + margin): the level of q = -2 power below which alpha >= 1/255 is possible
-    // (see cull_keep); -1 when the opacity alone rules it out, +inf for a degenerate conic
-    float q2tau;
-    const float tau = __logf(255.0f * co.w) + 0.02f;
-    const float det = co.x * co.z - co.y * co.y;
-    if (!(tau > 0.0f)) q2tau = -1.0f;
-    else if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f) || !isfinite(det) || !isfinite(tau)) q2tau = 3.0e38f;
-    else q2tau = 2.0f * tau;
-    const size_t o = (size_t)range.x + i;
-    b.point_list[o] = id;
-    b.inst_geo[o] = make_float4(xy.x, xy.y, q2tau, 0.0f);
-    b.inst_attr[2 * o] = co;
-    b.inst_attr[2 * o + 1] = make_float4(colors[3 * id], colors[3 * id + 1], colors[3 * id + 2], __uint_as_float(id));
+    pack_run(s_keys, cnt, (size_t)range.x + start, g, colors, b, tid);
+    k0 = k1;
+    if (k0 < DEPTH_BUCKETS) __syncthreads();  // the stage is overwritten by the next run
   }
 }
 
@@ -785,20 +844,10 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
              (const uint32_t*)im.depth_range, b.keys, gx, gy, (const int32_t*)a.status, use_hint, a.hint_lo, a.hint_hi);
   g_prof.end(2, s);
   g_prof.begin(3, s);
-  {
-    // shared-memory capacity of the per-tile sort: the default holds 6016 keys at four CTAs per SM; a frame
-    // whose longest tile list (hinted by the previous frame) is longer gets 24576 keys at one CTA per SM
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(tile_sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           SORT_SMEM_KEYS_BIG * (int)sizeof(unsigned long long));
-      attr = true;
-    }
-    const uint32_t cap = (a.hint_max_tile > SORT_SMEM_KEYS) ? SORT_SMEM_KEYS_BIG : SORT_SMEM_KEYS;
-    launch_pdl(tile_sort_pack_kernel, dim3(T), dim3(256), cap * sizeof(unsigned long long), s,
-               (const uint2*)im.ranges, b.keys, (const uint32_t*)im.hist, g, a.colors_precomp, b,
-               (const int32_t*)a.status, cap);
-  }
+  // (a.hint_max_tile is advisory and no longer needed: the kernel walks a tile in stage-sized runs)
+  launch_pdl(tile_sort_pack_kernel, dim3(T), dim3(256), 0, s, (const uint2*)im.ranges,
+             (const uint32_t*)im.tile_order, b.keys, (const uint32_t*)im.hist, g, a.colors_precomp, b,
+             (const int32_t*)a.status);
   g_prof.end(3, s);
   return cudaGetLastError();
 }

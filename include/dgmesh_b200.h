@@ -97,8 +97,8 @@ int dgr_workspace_sizes(int P, int W, int H, int64_t R_cap,
  * status[DGR_ST_DEPTH_LO/HI]) lets preprocess build the (tile, depth-bucket) histogram
  * itself (one kernel less); the hint only affects bucket balance, never the result.
  * Pass 0, 0 when there is none.  max_tile_hint (status[DGR_ST_MAX_TILE] of an earlier frame, 0 = unknown)
- * selects the shared-memory capacity of the per-tile sort (object-filling scenes have lists of >6016 keys);
- * like the depth hint it affects speed only. */
+ * is advisory: like the depth hint it can only affect speed (the per-tile sort walks a list of any
+ * length in 3072-key shared-memory stages and currently ignores it). */
 int dgr_forward(int P, int D, int M,
                 const float* background, int W, int H,
                 const float* means3D, const float* shs, const float* colors_precomp,

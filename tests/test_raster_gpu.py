@@ -167,7 +167,7 @@ def test_bit_exact_against_reference(n, W, H, degree, colors, cov, scale):
 
 @needs_ref
 def test_long_tile_list_global_sort_path():
-    """More instances in one tile than the shared-memory sort holds (6016)."""
+    """More instances in one tile than one shared-memory sort stage holds (3072): several runs per tile."""
     n = 9000
     sc, cam = util.small_scene(n=n, W=64, H=64, seed=2, scale=0.02)
     sc["means3D"] = sc["means3D"] * 0.02  # everything lands on the centre tiles
@@ -183,9 +183,9 @@ def test_long_tile_list_global_sort_path():
 @needs_ref
 def test_object_shaped_scene_dense_tiles_all_sort_regimes():
     """What DG-Mesh actually trains on: an object filling a fraction of the image -- thousands of instances per tile
-    inside a narrow depth range, i.e. depth buckets of hundreds to thousands of keys.  Exercises the warp-cooperative
-    and CTA-wide block sorts, the 24 576-key shared-memory variant (second call: chosen from the first call's
-    longest-tile hint) and the in-place global path; lists stay bit-exact."""
+    inside a narrow depth range, i.e. depth buckets of hundreds to thousands of keys.  Exercises the register, the
+    warp-cooperative and the CTA-wide block sorts and tiles walked in several stage-sized runs (first call without,
+    second call with the previous frame's hints); lists stay bit-exact."""
     import diff_gaussian_rasterization as dgr
     n = 40000
     sc, cam = util.small_scene(n=n, W=160, H=128, seed=3, scale=0.02)
@@ -201,10 +201,31 @@ def test_object_shaped_scene_dense_tiles_all_sort_regimes():
     b = run_ref(sc, cam, bg, 3, False, False, dpix)
     lens = (b["ranges"][:, 1] - b["ranges"][:, 0])
     assert int(lens.max()) > 6016 and int((lens > 2048).sum()) >= 4, lens.max()
-    for attempt in ("no hint: default shared memory, long lists in global memory", "hinted: 24576-key shared memory"):
+    for attempt in ("no hint", "hinted"):
         a = run_ours(sc, cam, bg, 3, False, False, dpix)
         compare(a, b, label=f"object scene ({attempt})")
     assert dgr._Sizing.hint[(torch.cuda.current_device(), 160, 128)][3] == int(lens.max())
+
+
+@needs_ref
+def test_one_depth_plane_block_longer_than_the_sort_stage():
+    """Thousands of Gaussians at (almost) ONE view depth on a few tiles: a single depth block longer than the 3072-key
+    stage is sorted in place in global memory.  A few far-away Gaussians keep the frame's depth range wide."""
+    n = 6000
+    sc, cam = util.small_scene(n=n, W=64, H=64, seed=4, scale=0.02)
+    g = torch.Generator().manual_seed(9)
+    V = cam.world_view_transform                       # row-vector convention: [p, 1] @ V = view-space point
+    pv = torch.cat([0.05 * torch.randn(n, 2, generator=g), torch.full((n, 1), 4.0), torch.ones(n, 1)], 1)
+    pv[:, 2] += 1e-6 * torch.randn(n, generator=g)     # depths differ in the last bits only
+    pv[-8:, 2] = torch.linspace(2.0, 8.0, 8)           # the frame's depth range
+    sc["means3D"] = (pv @ torch.linalg.inv(V))[:, :3].contiguous()
+    sc["opacities"] = sc["opacities"] * 0.05
+    sc, cam = _cuda(sc), _cam_cuda(cam)
+    bg = torch.zeros(3, device="cuda")
+    dpix = torch.randn(3, 64, 64, generator=torch.Generator().manual_seed(3)).cuda()
+    a, b = run_ours(sc, cam, bg, 3, False, False, dpix), run_ref(sc, cam, bg, 3, False, False, dpix)
+    assert int((b["ranges"][:, 1] - b["ranges"][:, 0]).max()) > 3500
+    compare(a, b, label="one-depth plane")
 
 
 @needs_ref

@@ -13,6 +13,8 @@
 //   T0 [Pp, 16], T1 [Pp, 256] (timenet), H[l] [Pp, 256]
 // Training keeps every activation (they double as the MN-major operands of the weight-gradient
 // GEMMs -- no transposed copies); inference ping-pongs two buffers.
+#include <stdlib.h>
+
 #include "mlp_gemm.cuh"
 #include "mlp_kernels.h"
 
@@ -38,11 +40,20 @@ static int sm_count() {
 cudaError_t launch_layer_gemm(const LayerArgs& g, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(layer_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_SMEM);
+    cudaFuncSetAttribute(layer_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_SMEM);
+    cudaFuncSetAttribute(layer_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LGR_SMEM);
     attr = true;
   }
   if (g.tiles <= 0) return cudaSuccess;
-  layer_gemm_kernel<<<min(g.tiles, sm_count()), LG_THREADS, LG_SMEM, s>>>(g);
+  // weights that fit 128 KB stay in shared memory for the CTA's lifetime (every 256-wide layer); the skip layer
+  // (K = 320) streams them.  DGMESH_B200_MLP_STREAM=1 forces the streaming variant (A/B comparison).
+  static const bool force_stream = [] {
+    const char* e = getenv("DGMESH_B200_MLP_STREAM");
+    return e && e[0] == '1';
+  }();
+  const bool resident = !force_stream && (size_t)(g.K >> 3) * g.N * 16 <= LGR_B_BYTES;
+  if (resident) layer_gemm_kernel<true><<<min(g.tiles, sm_count()), LG_THREADS, LGR_SMEM, s>>>(g);
+  else layer_gemm_kernel<false><<<min(g.tiles, sm_count()), LG_THREADS, LG_SMEM, s>>>(g);
   return cudaGetLastError();
 }
 

@@ -67,23 +67,40 @@ struct LayerArgs {
 #define LG_B_BYTES (256 * 64 * 2)    // 32 KB: up to 256 rows x 64 K
 #define LG_THREADS 320  // producer warp + MMA warp + 8 epilogue warps
 #define LG_SMEM (LG_STAGES * (LG_A_BYTES + LG_B_BYTES) + 1024)
+// RESIDENT variant (RES = true; whenever the weight matrix fits 128 KB, i.e. every 256x256 layer): measured on the
+// streaming variant, a layer moved 704 KB per 128-row tile through L2 (the weights re-fetched by every tile and
+// pass) -- ~11 TB/s, the L2 slices' throughput limit, while HBM sat at 39 %.  Here B (B_hi in split precision)
+// is loaded into shared memory ONCE per CTA; the ring carries only what changes per tile, in 16 KB stages:
+//   single pass        one 64-wide K chunk of A
+//   split precision    one 16-wide K step of A_hi, A_lo and B_lo -- the three products of a K step are issued
+//                      back to back (A_hi B_hi, A_lo B_hi, A_hi B_lo), so A_hi is fetched once, not twice
+// L2 traffic per tile: 704 -> 384 KB (split precision), 256 -> 128 KB (single pass).
+#define LGR_B_BYTES 131072
+#define LGR_STAGES 5
+#define LGR_STAGE_BYTES 16384
+#define LGR_SMEM (LGR_B_BYTES + LGR_STAGES * LGR_STAGE_BYTES + 1024)
+#define LG_MAX_STAGES 5
 
+template <bool RES>
 __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_full[LG_STAGES], s_empty[LG_STAGES], s_acc_full[2], s_acc_empty[2];
+  __shared__ __align__(8) uint64_t s_full[LG_MAX_STAGES], s_empty[LG_MAX_STAGES], s_acc_full[2], s_acc_empty[2], s_bres;
   __shared__ uint32_t s_tmem;
   __shared__ float s_bias[256];
+  constexpr int NST = RES ? LGR_STAGES : LG_STAGES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 1 KB aligned operand ring
-  const uint32_t sA = ring, sB = ring + LG_STAGES * LG_A_BYTES;
+  const uint32_t sA = ring, sB = ring + LG_STAGES * LG_A_BYTES;  // streaming variant
+  const uint32_t sBres = ring, sStage = ring + LGR_B_BYTES;      // resident variant
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < LG_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 1);
     }
+    mbar_init(&s_bres, 1);
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_acc_full[b], 1);
@@ -105,7 +122,40 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
 
   if (warp == 0) {
     // ------------------------------------------------------------ producer
-    if (lane == 0) {
+    if (RES && lane == 0) {
+      if (my_tiles > 0) {  // the resident weights, once
+        const uint32_t bytes = (uint32_t)nkb * g.N * 16;
+        mbar_expect_tx(&s_bres, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u)
+          tma_load_1d_u32(sBres + off, reinterpret_cast<const uint8_t*>(g.B) + off, min(32768u, bytes - off), &s_bres);
+      }
+      uint32_t it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const size_t a_off = (size_t)tile * g.A.tile_stride + (size_t)g.A.kb0 * KB_ELEMS;
+        if (npasses == 1) {
+          for (int c = 0; c < nchunks; ++c, ++it) {
+            const int st = it % NST;
+            const int kbs = min(8, nkb - 8 * c);
+            mbar_wait(&s_empty[st], ((it / NST) & 1) ^ 1);
+            const uint32_t a_bytes = kbs * (ACT_R * 16);
+            mbar_expect_tx(&s_full[st], a_bytes);
+            tma_load_1d_u32(sStage + st * LGR_STAGE_BYTES, g.A.p + a_off + (size_t)c * 8 * KB_ELEMS, a_bytes, &s_full[st]);
+          }
+        } else {
+          const uint32_t bl_bytes = (uint32_t)g.N * 32;  // two k blocks of B_lo
+          for (int c = 0; c < (nkb >> 1); ++c, ++it) {
+            const int st = it % NST;
+            mbar_wait(&s_empty[st], ((it / NST) & 1) ^ 1);
+            mbar_expect_tx(&s_full[st], 2 * 4096u + bl_bytes);
+            const uint32_t dst = sStage + st * LGR_STAGE_BYTES;
+            tma_load_1d_u32(dst, g.A.p + a_off + (size_t)c * 2 * KB_ELEMS, 4096u, &s_full[st]);
+            tma_load_1d_u32(dst + 4096u, g.A_lo + a_off + (size_t)c * 2 * KB_ELEMS, 4096u, &s_full[st]);
+            tma_load_1d_u32(dst + 8192u, g.B_lo + (size_t)c * 2 * g.N * 8, bl_bytes, &s_full[st]);
+          }
+        }
+      }
+    } else if (!RES && lane == 0) {
       uint32_t it = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
@@ -137,6 +187,40 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
         mbar_wait(&s_acc_empty[buf], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         umma::fence_after_sync();
         const uint32_t d_tmem = tmem + buf * 256;
+        if (RES) {
+          if (i == 0) mbar_wait(&s_bres, 0);
+          if (npasses == 1) {
+            for (int c = 0; c < nchunks; ++c, ++it) {
+              const int st = it % NST;
+              const int kbs = min(8, nkb - 8 * c);
+              mbar_wait(&s_full[st], (it / NST) & 1);
+              umma::fence_after_sync();
+              for (int ks = 0; ks < (kbs >> 1); ++ks) {
+                const uint64_t da = umma::smem_desc(sStage + st * LGR_STAGE_BYTES + ks * 2 * (ACT_R * 16), ACT_R * 16, 128);
+                const uint64_t db = umma::smem_desc(sBres + (uint32_t)(c * 8 + ks * 2) * lbo_b, lbo_b, 128);
+                umma::mma_bf16(d_tmem, da, db, idesc, (c | ks) != 0);
+              }
+              umma::commit(&s_empty[st]);
+            }
+          } else {
+            for (int c = 0; c < (nkb >> 1); ++c, ++it) {
+              const int st = it % NST;
+              mbar_wait(&s_full[st], (it / NST) & 1);
+              umma::fence_after_sync();
+              const uint32_t base = sStage + st * LGR_STAGE_BYTES;
+              const uint64_t da_hi = umma::smem_desc(base, ACT_R * 16, 128);
+              const uint64_t da_lo = umma::smem_desc(base + 4096u, ACT_R * 16, 128);
+              const uint64_t db_hi = umma::smem_desc(sBres + (uint32_t)(2 * c) * lbo_b, lbo_b, 128);
+              const uint64_t db_lo = umma::smem_desc(base + 8192u, lbo_b, 128);
+              umma::mma_bf16(d_tmem, da_hi, db_hi, idesc, c != 0);
+              umma::mma_bf16(d_tmem, da_lo, db_hi, idesc, true);
+              umma::mma_bf16(d_tmem, da_hi, db_lo, idesc, true);
+              umma::commit(&s_empty[st]);
+            }
+          }
+          umma::commit(&s_acc_full[buf]);
+          continue;
+        }
         for (int pc = 0; pc < npasses * nchunks; ++pc, ++it) {
           const int c = pc % nchunks;
           const int st = it % LG_STAGES;

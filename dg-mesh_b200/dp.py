@@ -98,7 +98,8 @@ class NvlsFlatGrad(FlatGrad):
     no multicast support (use `FlatGrad` there).  torch's symmetric-memory allocator is plumbing: it provides
     the memory, the multicast address and the signal pads; the collective itself is ours."""
 
-    BLOCKS = 32
+    BLOCKS = 296     # two per SM: enough multimem requests in flight to fill the links
+    PAD_SKIP = 128
 
     def __init__(self, params, group=None):
         self.group = group
@@ -119,8 +120,7 @@ class NvlsFlatGrad(FlatGrad):
         group = self.group if self.group is not None else dist.group.WORLD
         buf = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)
         self._handle = symm_mem.rendezvous(buf, group)
-        if not self._handle.has_multicast_support() if callable(getattr(self._handle, "has_multicast_support", None)) \
-                else not self._handle.multicast_ptr:
+        if not int(self._handle.multicast_ptr):
             raise RuntimeError("NvlsFlatGrad: no NVSwitch multicast support on this platform; use FlatGrad (NCCL)")
         buf.zero_()
         self._buf = buf
@@ -131,8 +131,10 @@ class NvlsFlatGrad(FlatGrad):
             self.shapes.append(tuple(p.shape))
             off += p.numel()
         self._bind(copy=False)
-        pad_words = int(self._handle.signal_pad_size) // 4
-        self._blocks = max(1, min(self.BLOCKS, pad_words // max(1, self._handle.world_size)))
+        pad_words = int(self._handle.signal_pad_size) // 4 - self.PAD_SKIP      # csrc/nvls_kernels.h NVLS_PAD_SKIP
+        if pad_words < self._handle.world_size:
+            raise RuntimeError("NvlsFlatGrad: signal pad too small")
+        self._blocks = self.BLOCKS
         self._handle.barrier()      # everyone's buffer and pads exist (and are zero) before the first kernel
 
     def allreduce(self, average=True, group=None):

@@ -12,7 +12,8 @@ outputs agree with the fp32 reference to ~1e-5 and the ReLU decisions are the re
 backward is single-pass bf16 and the parameter / input gradients agree to <= 2 % relative L2
 (measured 0.3-1 %).  `bf16`: single-pass forward, 3x fewer MMAs; outputs ~2e-3, but ~1 % of the
 ReLU signs flip and gradients differ by ~7 % (tests/test_mlp.py).  is_6dof (off in every
-reference config) is not implemented and raises.
+reference config): branch_w / branch_v run as one 6-row head of the same kernel chain, the SE(3) exponential
+(utils/rigid_utils.py) is elementwise torch on the [N,6] result.
 
 The packed bf16 operands are cached per module and rebuilt only when a parameter changed (tensor
 version counters), i.e. once per optimiser step, not once per forward.
@@ -147,8 +148,6 @@ class _TimeNet(nn.Module):
         super().__init__()
         if D != 8 or W != 256 or multires != 10:
             raise NotImplementedError("time_utils (B200): D=8, W=256, multires=10 (the reference defaults) only")
-        if is_6dof:
-            raise NotImplementedError("time_utils (B200): is_6dof is not part of the hot path (off in all configs)")
         self.D, self.W, self.input_ch, self.output_ch = D, W, input_ch, output_ch
         self.t_multires = 6 if is_blender else 10
         self.skips = [D // 2]
@@ -165,16 +164,34 @@ class _TimeNet(nn.Module):
         self.linear = nn.ModuleList([nn.Linear(in0, W)] + [
             nn.Linear(W, W) if i not in self.skips else nn.Linear(W + in0, W) for i in range(D - 1)])
         self.is_blender, self.is_6dof = is_blender, is_6dof
+        # is_6dof (time_utils.py:96-98,169-171): the translation head is replaced by a screw axis (branch_w,
+        # branch_v); the kernel sees ONE 6-row head whose weights are the two branches stacked
+        self._screw = bool(is_6dof) and self.HEADS[0][0] == "gaussian_warp"
         self._make_heads(W)
-        self._spec = dict(blender=int(is_blender), in_t=in0 - xyz_input_ch, sigmoid=int(self.SIGMOID),
-                          heads=[r for _, r in self.HEADS])
+        rows = [r for _, r in self.HEADS]
+        if self._screw:
+            rows[0] = 6
+        self._spec = dict(blender=int(is_blender), in_t=in0 - xyz_input_ch, sigmoid=int(self.SIGMOID), heads=rows)
 
     def _make_heads(self, W):
         for name, rows in self.HEADS:
-            setattr(self, name, nn.Linear(W, rows))
+            if self._screw and name == "gaussian_warp":   # same construction order as the reference
+                self.branch_w = nn.Linear(W, 3)
+                self.branch_v = nn.Linear(W, 3)
+            else:
+                setattr(self, name, nn.Linear(W, rows))
 
-    def _head_modules(self):
-        return [getattr(self, n) for n, _ in self.HEADS]
+    def _head_params(self):
+        ps = []
+        for name, _ in self.HEADS:
+            if self._screw and name == "gaussian_warp":
+                ps += [torch.cat([self.branch_w.weight, self.branch_v.weight], 0),
+                       torch.cat([self.branch_w.bias, self.branch_v.bias], 0)]
+            else:
+                h = getattr(self, name)
+                h = h[0] if isinstance(h, nn.Sequential) else h
+                ps += [h.weight, h.bias]
+        return ps
 
     def _param_list(self):
         ps = []
@@ -182,16 +199,25 @@ class _TimeNet(nn.Module):
             ps += [self.timenet[0].weight, self.timenet[0].bias, self.timenet[2].weight, self.timenet[2].bias]
         for l in self.linear:
             ps += [l.weight, l.bias]
-        for h in self._head_modules():
-            ps += [h.weight, h.bias]
-        return ps
+        return ps + self._head_params()
+
+    def _warp(self, first):
+        """d_xyz from the first head: a translation, or (is_6dof) the SE(3) transform of a screw motion."""
+        if not self._screw:
+            return first
+        from utils.rigid_utils import exp_se3
+        w, v = first[:, :3], first[:, 3:6]
+        theta = torch.norm(w, dim=-1, keepdim=True)
+        w = w / theta + 1e-5                     # as written in the reference (time_utils.py:119-123)
+        v = v / theta + 1e-5
+        return exp_se3(torch.cat([w, v], dim=-1), theta)
 
     def _run(self, x, t):
         params = self._param_list()
         train = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         out = _MLPFunction.apply(self._spec, train, x, t, *params)
         cols, o = [], 0
-        for _, r in self.HEADS:
+        for r in self._spec["heads"]:
             cols.append(out[:, o:o + r])
             o += r
         return cols
@@ -202,7 +228,7 @@ class DeformNetwork(_TimeNet):
 
     def forward(self, x, t):
         d_xyz, rotation, scaling = self._run(x, t)
-        return d_xyz, rotation, scaling
+        return self._warp(d_xyz), rotation, scaling
 
 
 class DeformNetworkNormal(_TimeNet):
@@ -211,7 +237,7 @@ class DeformNetworkNormal(_TimeNet):
 
     def forward(self, x, t):
         d_xyz, rotation, scaling, normal = self._run(x, t)
-        return d_xyz, rotation, scaling, normal
+        return self._warp(d_xyz), rotation, scaling, normal
 
 
 class DeformNetworkNormalSep(_TimeNet):
@@ -235,9 +261,6 @@ class AppearanceNetwork(_TimeNet):
 
     def _make_heads(self, W):
         self.color_warp = nn.Sequential(nn.Linear(W, 3), nn.Sigmoid())   # time_utils.py:306-309
-
-    def _head_modules(self):
-        return [self.color_warp[0]]
 
     def forward(self, x, t):
         return self._run(x, t)[0]

@@ -191,6 +191,45 @@ def test_mlp_inference_mode_and_errors():
     b = torch.cat(net(x.cuda(), t.cuda()), -1)          # training path
     assert torch.equal(a, b.detach())
     with pytest.raises(NotImplementedError):
-        tu.DeformNetworkNormal(is_6dof=True)
+        tu.DeformNetworkNormal(D=6)
     with pytest.raises(ValueError):
         net(x, t)                                        # CPU tensors: no fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls", ["DeformNetwork", "DeformNetworkNormal"])
+def test_is_6dof_screw_motion_head_matches_reference(cls):
+    """`is_6dof=True` (time_utils.py:96-98,116-123): branch_w / branch_v replace the translation head and d_xyz is
+    the [N,4,4] SE(3) transform of the screw motion.  Same state_dict keys, outputs and gradients vs the reference's
+    fp32 module; `render(..., is_6dof=True)` consumes the transform through this repo's rigid_utils."""
+    tu = importlib.import_module("utils.time_utils")
+    torch.manual_seed(3)
+    mine = getattr(tu, cls)(is_blender=True, is_6dof=True).cuda()
+    theirs = getattr(ref.time_utils, cls)(is_blender=True, is_6dof=True).cuda()
+    assert set(mine.state_dict()) == set(theirs.state_dict())
+    theirs.load_state_dict(mine.state_dict())
+    x, t = inputs(1500, 6)
+    x, t = x.cuda(), t.cuda()
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    oa, ob = mine(xa, t), theirs(xb, t)
+    assert oa[0].shape == ob[0].shape == (1500, 4, 4)
+    la = lb = 0
+    for i, (a, b) in enumerate(zip(oa, ob)):
+        assert a.shape == b.shape
+        assert util.rel_l2(a, b) < 1e-4, i
+        g = torch.randn(a.shape, generator=torch.Generator().manual_seed(10 + i)).cuda()
+        la, lb = la + (a * g).sum(), lb + (b * g).sum()
+    la.backward()
+    lb.backward()
+    errs = {"dx": util.rel_l2(xa.grad, xb.grad)}
+    pa, pb = dict(mine.named_parameters()), dict(theirs.named_parameters())
+    for k in pa:
+        errs[k] = util.rel_l2(pa[k].grad, pb[k].grad)
+    bad = {k: v for k, v in errs.items() if v > 2e-2}
+    assert not bad, bad
+    # the renderer's use of the transform (gaussian_renderer/__init__.py:68-73)
+    import utils.rigid_utils as ru
+    p = torch.randn(1500, 3, device="cuda")
+    moved = ru.from_homogenous(torch.bmm(oa[0].detach(), ru.to_homogenous(p).unsqueeze(-1)).squeeze(-1))
+    want = ref.rigid_utils.from_homogenous(torch.bmm(ob[0].detach(), ref.rigid_utils.to_homogenous(p).unsqueeze(-1)).squeeze(-1))
+    assert util.rel_l2(moved, want) < 1e-4

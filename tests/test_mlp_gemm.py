@@ -43,7 +43,7 @@ def run(M, N, K, bias=False, relu=False, lda=None, ldb=None):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 256), (128, 32, 64), (300, 256, 96), (1000, 16, 256), (257, 96, 352),
-                                   (4096, 256, 256), (128, 256, 16), (100_000, 256, 256), (50_000, 13, 256),
+                                   (4096, 256, 256), (128, 256, 16), (100_000, 256, 256), (50_000, 13, 256), (300, 256, 352),
                                    (777, 30, 250)])
 def test_layer_gemm_matches_torch(M, N, K):
     C, ref = run(M, N, K)

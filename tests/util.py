@@ -161,6 +161,8 @@ def load_reference_pymodules():
         sys.modules[f"refpy.{sub}"] = m
         spec.loader.exec_module(m)
         setattr(pkg, sub, m)
+    # the reference modules have bound what they need; from here on `utils.rigid_utils` is this repo's again
+    pkg.rigid_utils = sys.modules.pop("utils.rigid_utils")
     return pkg
 
 

@@ -43,6 +43,7 @@ SIGNATURES = {
     "dgr_export_state": (c_int, [c_int, c_int, c_int, c_int64, P, P, P] + [P] * 12 + [P]),
     "dgk_workspace_size": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
     "dgk_dist2": (c_int, [c_int, P, P, P, c_size_t, P]),
+    "dgk_nearest": (c_int, [c_int, P, c_int, P, P, P, P]),
     "dgp_plan_create": (c_int, [c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t)]),
     "dgp_plan_destroy": (c_int, [P]),
     "dgp_forward": (c_int, [P, c_int, ctypes.c_double, P, P, c_int, P, P, P, c_size_t, P]),

@@ -441,6 +441,13 @@ int dgk_dist2(int P, const float* points, float* mean_dist2, void* ws, size_t ws
   return check(dgm::launch_knn(P, points, mean_dist2, ws, (cudaStream_t)stream));
 }
 
+int dgk_nearest(int Q, const float* queries, int R, const float* refs, float* dist2, int64_t* index, void* stream) {
+  if (Q < 0 || R < 1) return bad("dgk_nearest: Q >= 0 and R >= 1 required");
+  if (Q == 0) return DGM_OK;
+  if (!queries || !refs || !dist2 || !index) return bad("dgk_nearest: null pointer");
+  return check(dgm::launch_nearest(Q, queries, R, refs, dist2, (long long*)index, (cudaStream_t)stream));
+}
+
 int dgp_plan_create(int G, void** plan, size_t* ws_bytes) {
   if (G < 4 || (G & 1) || !plan) return bad("dgp_plan_create: G must be even and >= 4");
   size_t work = 0;

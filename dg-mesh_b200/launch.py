@@ -45,7 +45,7 @@ def _merged_package(name, dirs):
 
 class _PatchScene:
     """meta-path hook: after `scene.gaussian_model_dpsr_dynamic_anchor` has been imported, swap in the
-    fused densify_and_prune."""
+    fused densify_and_prune and the device-side anchor_mesh."""
 
     def find_spec(self, fullname, path=None, target=None):
         if fullname != "scene.gaussian_model_dpsr_dynamic_anchor":
@@ -65,8 +65,10 @@ class _PatchScene:
 
             def exec_module(self, module):
                 inner.exec_module(module)
+                import anchor
                 import densify
                 densify.install(module.GaussianModelDPSRDynamicAnchor)
+                anchor.install(module.GaussianModelDPSRDynamicAnchor)
 
         spec.loader = Loader()
         return spec

@@ -224,6 +224,13 @@ int dgk_workspace_size(int P, size_t* bytes);
 int dgk_dist2(int P, const float* points, float* mean_dist2,
               void* ws, size_t ws_bytes, void* stream);
 
+/* Cross-set nearest neighbour, K = 1: for every query the squared distance to, and the index of, its
+ * nearest reference point (ties: lowest index).  Replaces `pytorch3d.ops.knn_points(p1, p2, K=1)` as
+ * anchor_mesh calls it (dgmesh/scene/gaussian_model_dpsr_dynamic_anchor.py:761): queries[Q,3],
+ * refs[R,3] fp32 -> dist2[Q] fp32, index[Q] int64.  R >= 1. */
+int dgk_nearest(int Q, const float* queries, int R, const float* refs,
+                float* dist2, int64_t* index, void* stream);
+
 /* ------------------------------------------------------------------------
  * DPSR -- differentiable Poisson surface reconstruction on a G^3 periodic grid.
  * replaces DPSR.forward (dgmesh/nvdiffrast_utils/dpsr.py:28-70) with point_rasterize /

@@ -152,6 +152,13 @@ def _make_trimesh():
             c = self._cross()
             return c / np.maximum(np.linalg.norm(c, axis=1, keepdims=True), 1e-20)
 
+        @property
+        def edges_unique_length(self):
+            f = self.faces
+            e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], 0), axis=1)
+            e = np.unique(e, axis=0)
+            return np.linalg.norm(self.vertices[e[:, 0]] - self.vertices[e[:, 1]], axis=1)
+
         def export(self, path=None, *a, **k):
             return None
 
@@ -181,16 +188,29 @@ def _make_pytorch3d():
     KNN = collections.namedtuple("KNN", "dists idx knn")
 
     def knn_points(p1, p2, K=1, **kw):
-        """exact brute force in chunks (pytorch3d.ops.knn_points returns squared distances)"""
+        """exact brute force in chunks from coordinate differences (pytorch3d.ops.knn_points returns squared
+        distances; differentiable w.r.t. both point sets like the original)"""
         dists, idxs = [], []
-        for chunk in p1[0].split(4096):
-            d = torch.cdist(chunk[None], p2) ** 2
+        step = max(1, (1 << 24) // max(1, p2.shape[1]))
+        for chunk in p1[0].split(step):
+            diff = chunk[:, None, :] - p2[0][None, :, :]
+            d = (diff * diff).sum(-1)
             dd, ii = d.topk(K, dim=-1, largest=False)
             dists.append(dd)
             idxs.append(ii)
-        return KNN(torch.cat(dists, 1), torch.cat(idxs, 1), None)
+        return KNN(torch.cat(dists, 0)[None], torch.cat(idxs, 0)[None], None)
 
     ops.knn_points = knn_points
+
+    def axis_angle_to_quaternion(axis_angle):
+        """pytorch3d.transforms.axis_angle_to_quaternion (published formula): (w, x, y, z), real part first"""
+        angles = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
+        half = 0.5 * angles
+        small = angles.abs() < 1e-6
+        k = torch.where(small, 0.5 - angles * angles / 48, torch.sin(half) / torch.where(small, torch.ones_like(angles), angles))
+        return torch.cat([torch.cos(half), axis_angle * k], dim=-1)
+
+    pkg.transforms.axis_angle_to_quaternion = axis_angle_to_quaternion
     return pkg, ops
 
 

@@ -106,6 +106,14 @@ def test_state_dicts_are_interchangeable_with_the_reference_cpu(cls, blender):
     theirs.load_state_dict(mine.state_dict(), strict=True)
     for k in sd_t:
         assert torch.equal(mine.state_dict()[k], sd_t[k])
-    # constructor surface
+    # constructor surface: unsupported trunk shapes raise; is_6dof has the reference's parameters, in its order
     with pytest.raises(NotImplementedError):
-        getattr(tu, "DeformNetwork")(is_6dof=True)
+        getattr(tu, "DeformNetwork")(D=4)
+    if cls in ("DeformNetwork", "DeformNetworkNormal"):
+        torch.manual_seed(3)
+        t6 = getattr(ref.time_utils, cls)(is_blender=blender, is_6dof=True)
+        torch.manual_seed(3)
+        m6 = getattr(tu, cls)(is_blender=blender, is_6dof=True)
+        assert list(t6.state_dict().keys()) == list(m6.state_dict().keys())
+        for k, v in t6.state_dict().items():
+            assert torch.equal(v, m6.state_dict()[k]), k       # same construction order -> same default init

@@ -324,7 +324,25 @@ class _BatchWorkspace:
         return w
 
 
+_stacked = {}   # camera tensors' (address, version) -> stacked copies: a training loop reuses its cameras
+
+
 def _stack_settings(settings, dev):
+    key = tuple((s.viewmatrix.data_ptr(), s.viewmatrix._version, s.projmatrix.data_ptr(), s.projmatrix._version,
+                 s.campos.data_ptr(), s.campos._version, float(s.tanfovx), float(s.tanfovy)) for s in settings)
+    hit = _stacked.get(key)
+    if hit is not None and not torch.cuda.is_current_stream_capturing():
+        return hit[0]
+    out = _stack_settings_uncached(settings, dev)
+    if len(_stacked) >= 8:
+        _stacked.clear()
+    # the entry keeps the source tensors alive: their addresses cannot be recycled for other cameras while the
+    # key is valid, and in-place updates move the version counters
+    _stacked[key] = (out, [(s.viewmatrix, s.projmatrix, s.campos) for s in settings])
+    return out
+
+
+def _stack_settings_uncached(settings, dev):
     views = torch.stack([_f32c(s.viewmatrix, "viewmatrix") for s in settings]).contiguous()
     projs = torch.stack([_f32c(s.projmatrix, "projmatrix") for s in settings]).contiguous()
     cams = torch.stack([_f32c(s.campos, "campos") for s in settings]).contiguous()

@@ -427,6 +427,52 @@ def test_per_frame_parameter_batch_equals_single_frames():
 
 
 
+def test_batch_camera_cache_follows_in_place_updates_and_new_tensors():
+    """The batch call caches its stacked camera matrices by (address, version): a camera buffer overwritten in
+    place (a data loader's staging slot) or replaced by a new tensor must render with the NEW camera."""
+    import diff_gaussian_rasterization as dgr
+    import synth
+    P = 3000
+    sc, _ = util.small_scene(n=P, W=96, H=64, seed=8, scale=0.05)
+    sc = _cuda(sc)
+    bg = torch.zeros(3, device="cuda")
+    mk = lambda az: _cam_cuda(synth.look_at_camera(azimuth_deg=az, elevation_deg=10.0, radius=4.0, width=96, height=64,  # noqa: E731
+                                                   fovx=0.6911, fovy=0.6911 * 64 / 96))
+    cams = [mk(0.0), mk(90.0)]
+    others = [mk(200.0), mk(300.0)]
+    stage = [(c.world_view_transform.clone(), c.full_proj_transform.clone(), c.camera_center.clone()) for c in cams]
+
+    def settings(ts):
+        return [synth.raster_settings_for(c, bg, settings_cls=dgr.GaussianRasterizationSettings)._replace(
+            viewmatrix=v, projmatrix=p, campos=cp) for c, (v, p, cp) in zip(cams, ts)]
+
+    def batch(sets):
+        with torch.no_grad():
+            return dgr.BatchGaussianRasterizer(sets)(means3D=sc["means3D"], means2D=None, opacities=sc["opacities"],
+                                                     shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])[0]
+
+    def single(c):
+        with torch.no_grad():
+            rs = synth.raster_settings_for(c, bg, settings_cls=dgr.GaussianRasterizationSettings)
+            return dgr.GaussianRasterizer(rs)(means3D=sc["means3D"], means2D=None, opacities=sc["opacities"],
+                                              shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])[0]
+
+    sets = settings(stage)
+    a = batch(sets)
+    assert torch.equal(a[0], single(cams[0])) and torch.equal(a[1], single(cams[1]))
+    assert torch.equal(batch(sets), a)                                    # cache hit: same result
+    for (v, p, cp), c in zip(stage, others):                              # overwrite the staging tensors in place
+        v.copy_(c.world_view_transform)
+        p.copy_(c.full_proj_transform)
+        cp.copy_(c.camera_center)
+    b = batch(sets)
+    assert torch.equal(b[0], single(others[0])) and torch.equal(b[1], single(others[1]))
+    del sets, stage                                                        # fresh tensors, possibly at recycled addresses
+    fresh = [(c.world_view_transform.clone(), c.full_proj_transform.clone(), c.camera_center.clone()) for c in cams]
+    c2 = batch(settings(fresh))
+    assert torch.equal(c2, a)
+
+
 def test_full_size_properties():
     """Size-independent properties at 100k / 800x800 (no reference needed)."""
     import synth

@@ -45,13 +45,15 @@ cudaError_t launch_layer_gemm(const LayerArgs& g, cudaStream_t s) {
     attr = true;
   }
   if (g.tiles <= 0) return cudaSuccess;
-  // weights that fit 128 KB stay in shared memory for the CTA's lifetime (every 256-wide layer); the skip layer
-  // (K = 320) streams them.  DGMESH_B200_MLP_STREAM=1 forces the streaming variant (A/B comparison).
+  // split-precision layers whose weights fit 128 KB keep B_hi in shared memory for the CTA's lifetime (every
+  // 256-wide layer; the K = 320 skip layer streams).  Single-pass launches (the backward, bf16 mode) stay on the
+  // streaming variant: measured, residency gains them nothing at 100k-200k points and costs a serialised 128 KB
+  // prologue per CTA at 10k.  DGMESH_B200_MLP_STREAM=1 forces the streaming variant everywhere (A/B comparison).
   static const bool force_stream = [] {
     const char* e = getenv("DGMESH_B200_MLP_STREAM");
     return e && e[0] == '1';
   }();
-  const bool resident = !force_stream && (size_t)(g.K >> 3) * g.N * 16 <= LGR_B_BYTES;
+  const bool resident = !force_stream && g.A_lo != nullptr && (size_t)(g.K >> 3) * g.N * 16 <= LGR_B_BYTES;
   if (resident) layer_gemm_kernel<true><<<min(g.tiles, sm_count()), LG_THREADS, LGR_SMEM, s>>>(g);
   else layer_gemm_kernel<false><<<min(g.tiles, sm_count()), LG_THREADS, LG_SMEM, s>>>(g);
   return cudaGetLastError();

@@ -67,14 +67,13 @@ struct LayerArgs {
 #define LG_B_BYTES (256 * 64 * 2)    // 32 KB: up to 256 rows x 64 K
 #define LG_THREADS 320  // producer warp + MMA warp + 8 epilogue warps
 #define LG_SMEM (LG_STAGES * (LG_A_BYTES + LG_B_BYTES) + 1024)
-// RESIDENT variant (RES = true; whenever the weight matrix fits 128 KB, i.e. every 256x256 layer): measured on the
-// streaming variant, a layer moved 704 KB per 128-row tile through L2 (the weights re-fetched by every tile and
-// pass) -- ~11 TB/s, the L2 slices' throughput limit, while HBM sat at 39 %.  Here B (B_hi in split precision)
-// is loaded into shared memory ONCE per CTA; the ring carries only what changes per tile, in 16 KB stages:
-//   single pass        one 64-wide K chunk of A
-//   split precision    one 16-wide K step of A_hi, A_lo and B_lo -- the three products of a K step are issued
-//                      back to back (A_hi B_hi, A_lo B_hi, A_hi B_lo), so A_hi is fetched once, not twice
-// L2 traffic per tile: 704 -> 384 KB (split precision), 256 -> 128 KB (single pass).
+// RESIDENT variant (RES = true; split-precision layers whose weight matrix fits 128 KB, i.e. every 256x256 layer):
+// measured on the streaming variant, such a layer moved 704 KB per 128-row tile through L2 (the weights
+// re-fetched by every tile and pass) -- ~11 TB/s, the L2 slices' throughput limit, while HBM sat at 39 %.  Here
+// B_hi is loaded into shared memory ONCE per CTA; the ring carries only what changes per tile, in 16 KB stages:
+// one 16-wide K step of A_hi, A_lo and B_lo -- the three products of a K step are issued back to back
+// (A_hi B_hi, A_lo B_hi, A_hi B_lo), so A_hi is fetched once, not twice.  L2 traffic per tile: 704 -> 384 KB.
+// (Single-pass launches gain nothing from residency -- measured -- and keep the streaming variant.)
 #define LGR_B_BYTES 131072
 #define LGR_STAGES 5
 #define LGR_STAGE_BYTES 16384
@@ -133,16 +132,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
         const size_t a_off = (size_t)tile * g.A.tile_stride + (size_t)g.A.kb0 * KB_ELEMS;
-        if (npasses == 1) {
-          for (int c = 0; c < nchunks; ++c, ++it) {
-            const int st = it % NST;
-            const int kbs = min(8, nkb - 8 * c);
-            mbar_wait(&s_empty[st], ((it / NST) & 1) ^ 1);
-            const uint32_t a_bytes = kbs * (ACT_R * 16);
-            mbar_expect_tx(&s_full[st], a_bytes);
-            tma_load_1d_u32(sStage + st * LGR_STAGE_BYTES, g.A.p + a_off + (size_t)c * 8 * KB_ELEMS, a_bytes, &s_full[st]);
-          }
-        } else {
+        {
           const uint32_t bl_bytes = (uint32_t)g.N * 32;  // two k blocks of B_lo
           for (int c = 0; c < (nkb >> 1); ++c, ++it) {
             const int st = it % NST;
@@ -189,20 +179,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
         const uint32_t d_tmem = tmem + buf * 256;
         if (RES) {
           if (i == 0) mbar_wait(&s_bres, 0);
-          if (npasses == 1) {
-            for (int c = 0; c < nchunks; ++c, ++it) {
-              const int st = it % NST;
-              const int kbs = min(8, nkb - 8 * c);
-              mbar_wait(&s_full[st], (it / NST) & 1);
-              umma::fence_after_sync();
-              for (int ks = 0; ks < (kbs >> 1); ++ks) {
-                const uint64_t da = umma::smem_desc(sStage + st * LGR_STAGE_BYTES + ks * 2 * (ACT_R * 16), ACT_R * 16, 128);
-                const uint64_t db = umma::smem_desc(sBres + (uint32_t)(c * 8 + ks * 2) * lbo_b, lbo_b, 128);
-                umma::mma_bf16(d_tmem, da, db, idesc, (c | ks) != 0);
-              }
-              umma::commit(&s_empty[st]);
-            }
-          } else {
+          {
             for (int c = 0; c < (nkb >> 1); ++c, ++it) {
               const int st = it % NST;
               mbar_wait(&s_full[st], (it / NST) & 1);

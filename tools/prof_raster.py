@@ -18,7 +18,7 @@ frames = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = torch.device("cuda", 0)
 sc, cams, dpix = bench.make_inputs(dev)
 dpix = [d.to(dev) for d in dpix]
-leaves, gflat = bench.flat_params(sc, dev)
+leaves, gflat, _ = bench.flat_params(sc, dev)
 bg = torch.ones(3, device=dev)
 bench.run_frames(dgr, synth, leaves, cams, dpix, bg, list(range(frames)))
 torch.cuda.synchronize()

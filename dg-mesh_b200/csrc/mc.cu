@@ -29,9 +29,17 @@
 
 namespace dgm {
 
-__constant__ unsigned char c_ntri[256];
-__constant__ signed char c_tri[256][MC_MAX_TRI * 3];
-__constant__ unsigned char c_edge_lo[12];
+// case tables in GLOBAL memory, read through the read-only path: the case index differs from lane to lane, and a
+// __constant__ access with divergent addresses is replayed once per distinct address (measured: the emit pass
+// spent most of its time there); L1-cached loads are not
+__device__ unsigned char g_ntri[256];
+__device__ signed char g_tri[256][MC_MAX_TRI * 3];
+__device__ __forceinline__ unsigned mc_ntri(unsigned cs) { return (cs == 0u || cs == 255u) ? 0u : __ldg(&g_ntri[cs]); }
+// corner of edge e = 4 * axis + combo with the lower index (MC_EDGE_LO of mc_tables.h, in closed form)
+__device__ __forceinline__ int mc_edge_lo(int e) {
+  const int axis = e >> 2, k = e & 3;
+  return axis == 0 ? (k << 1) : (axis == 1 ? ((k & 1) | ((k & 2) << 1)) : k);
+}
 
 #define MC_WARPS 8  // bricks (warps) per CTA
 #define MC_BJ 8     // j-rows per brick
@@ -118,12 +126,38 @@ __global__ void __launch_bounds__(32 * MC_WARPS) mc_count_kernel(McGeom g, const
   if (brick >= g.nbricks) return;
   McBrick B;
   mc_load_brick(g, brick, lane, phi, B);
+  // the common case (>95 % of a 288^3 grid): every value the brick touches lies on one side of the level set --
+  // nothing to classify.  Lanes look at their own valid values (lane 31 also at its k + 1 column).
+  {
+    bool neg = false, pos = false;
+#pragma unroll
+    for (int r = 0; r <= MC_BJ; ++r) {
+      const bool jin = B.j0 + r < g.G;
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const bool ok = jin && B.kin && (pl == 0 || B.xi);
+        const bool s = B.a[pl][r] < iso;
+        neg |= ok && s;
+        pos |= ok && !s;
+        if (lane == 31) {
+          const bool okz = jin && B.zk && (pl == 0 || B.xi);
+          const bool sz = B.z[pl][r] < iso;
+          neg |= okz && sz;
+          pos |= okz && !sz;
+        }
+      }
+    }
+    if (!(__any_sync(0xffffffffu, neg) && __any_sync(0xffffffffu, pos))) {
+      if (lane == 0) blk_counts[brick] = 0ull;
+      return;
+    }
+  }
   unsigned c = 0;  // vertices | triangles << 16: <= 768 / 1280 per brick
 #pragma unroll
   for (int r = 0; r < MC_BJ; ++r) {
     unsigned mask, cs;
     mc_classify(g, B, r, iso, mask, cs);
-    c += __popc(mask) | ((unsigned)c_ntri[cs] << 16);
+    c += __popc(mask) | (mc_ntri(cs) << 16);
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -159,7 +193,7 @@ __global__ void __launch_bounds__(32 * MC_WARPS) mc_emit_kernel(
     unsigned mask;
     mc_classify(g, B, r, iso, mask, css[r]);
     masks |= mask << (3 * r);
-    mine += __popc(mask) | ((unsigned)c_ntri[css[r]] << 16);
+    mine += __popc(mask) | (mc_ntri(css[r]) << 16);
   }
   unsigned inc = mine;  // inclusive prefix over the lanes (order inside the brick: lane-major, then r)
 #pragma unroll
@@ -201,13 +235,13 @@ __global__ void __launch_bounds__(32 * MC_WARPS) mc_emit_kernel(
         }
       }
     }
-    const int nt = c_ntri[cs];
+    const int nt = (int)mc_ntri(cs);
     for (int t = 0; t < nt; ++t, ++f) {
       if ((long long)f >= F_cap) break;
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const int e = c_tri[cs][3 * t + q];
-        const int c = c_edge_lo[e], axis = e >> 2;
+        const int e = __ldg(&g_tri[cs][3 * t + q]);
+        const int c = mc_edge_lo(e), axis = e >> 2;
         const size_t owner = ((size_t)(B.i + (c & 1)) * G + (j + ((c >> 1) & 1))) * G + (B.k + (c >> 2));
         faces[3 * f + q] = (int32_t)(owner * 3 + axis);  // resolved by mc_resolve_kernel
       }
@@ -248,9 +282,13 @@ __global__ void __launch_bounds__(256) mc_backward_kernel(int G, int V, const fl
 static bool g_tables_uploaded = false;
 static cudaError_t upload_tables() {
   if (g_tables_uploaded) return cudaSuccess;
-  cudaError_t e = cudaMemcpyToSymbol(c_ntri, MC_NTRI, sizeof(MC_NTRI));
-  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_tri, MC_TRI, sizeof(MC_TRI));
-  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_edge_lo, MC_EDGE_LO, sizeof(MC_EDGE_LO));
+  cudaError_t e = cudaMemcpyToSymbol(g_ntri, MC_NTRI, sizeof(MC_NTRI));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tri, MC_TRI, sizeof(MC_TRI));
+  for (int i = 0; i < 12 && e == cudaSuccess; ++i) {  // the closed form must be the generated table
+    const int axis = i >> 2, k = i & 3;
+    const int lo = axis == 0 ? (k << 1) : (axis == 1 ? ((k & 1) | ((k & 2) << 1)) : k);
+    if (lo != MC_EDGE_LO[i]) e = cudaErrorInvalidValue;
+  }
   g_tables_uploaded = (e == cudaSuccess);
   return e;
 }

@@ -79,6 +79,10 @@ struct MlpBufs {
   float* dE;                            // [Pp, 96] fp32 row-major: gradient w.r.t. the embedded inputs
   // split-precision forward: rounding residuals of A5 / T0 / T1 and of the running hidden activation
   __nv_bfloat16 *A5lo, *T0lo, *T1lo, *Hlo[2];
+  // uniform-time shortcut: tu[0] = 1 when every row has the same t (decided on the device), tu[1] = tiles the
+  // time-net kernels process (1 or all); tsum[32] = column sums of the time-feature gradients
+  int* tu;
+  float* tsum;
   int Pp, tiles;
   static MlpBufs carve_all(char* base, int P, int train, size_t* bytes) {
     char* p = base;
@@ -94,6 +98,8 @@ struct MlpBufs {
     b.T1lo = carve<__nv_bfloat16>(p, Pp * WID);
     b.Hlo[0] = carve<__nv_bfloat16>(p, Pp * WID);
     b.Hlo[1] = carve<__nv_bfloat16>(p, Pp * WID);
+    b.tu = carve<int>(p, 32);
+    b.tsum = carve<float>(p, 32);
     if (train) {
       for (int l = 0; l < 8; ++l) b.H[l] = (l == 4) ? b.A5 : carve<__nv_bfloat16>(p, Pp * WID);
       for (int i = 0; i < 2; ++i) b.dZ[i] = carve<__nv_bfloat16>(p, Pp * WID);
@@ -232,8 +238,10 @@ __global__ void __launch_bounds__(256) sigmoid_kernel(int n, float* __restrict__
 }
 
 // dE[:, 64:96] (fp32 row-major) -> dZt1 blocked [Pp, 32] (features >= n_t are zero)
-__global__ void __launch_bounds__(256) tfeat_grad_kernel(int Pp, int n_t, const float* __restrict__ dE,
+__global__ void __launch_bounds__(256) tfeat_grad_kernel(int Pp, int n_t, const int* __restrict__ tu,
+                                                         const float* __restrict__ dE,
                                                          __nv_bfloat16* __restrict__ dZ) {
+  if (tu[0]) return;  // uniform time: tfeat_colsum / tfeat_row0 produce the single row that matters
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Pp) return;
   float v[32];
@@ -264,6 +272,70 @@ __global__ void __launch_bounds__(256) pe_backward_kernel(int P, const float* __
   }
 }
 
+// ---- uniform time: DG-Mesh evaluates a network at ONE time for all points of a frame (train.py:158-172:
+// fid.expand(N, -1), plus at most one shared noise scalar).  The time-net (t -> 256 -> 30 features) then produces
+// the same row N times: ~8 % of an MLP evaluation at 200k points, all of it HBM traffic.  The decision is made on
+// the device (no host read, exact in both cases): when every t equals t[0] the time-net kernels process tile 0
+// only and the 30 features are broadcast to all rows; in the backward the rows' feature gradients are summed
+// into row 0 first (the time-net is shared, so the sum of per-row backward passes is the backward of the sum).
+__global__ void __launch_bounds__(1024) t_uniform_kernel(int P, int tiles, const float* __restrict__ t,
+                                                         int* __restrict__ tu, float* __restrict__ tsum) {
+  const uint32_t t0 = __float_as_uint(t[0]);
+  int diff = 0;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) diff |= (__float_as_uint(t[p]) != t0);
+  diff = __syncthreads_or(diff);
+  if (threadIdx.x == 0) {
+    tu[0] = diff ? 0 : 1;
+    tu[1] = diff ? tiles : 1;
+  }
+  if (threadIdx.x < 32) tsum[threadIdx.x] = 0.f;
+}
+
+// time features of row 0 (A5 k-blocks TCOL/8 .. +3, hi and lo) -> every other row
+__global__ void __launch_bounds__(256) tfeat_broadcast_kernel(int Pp, const int* __restrict__ tu,
+                                                              __nv_bfloat16* __restrict__ A5,
+                                                              __nv_bfloat16* __restrict__ A5lo) {
+  if (!tu[0]) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (p >= Pp) return;
+#pragma unroll
+  for (int kb = TCOL / 8; kb < K0 / 8; ++kb) {
+    *blk_unit(A5, K5, p, kb) = *blk_unit(A5, K5, 0, kb);
+    if (A5lo) *blk_unit(A5lo, K5, p, kb) = *blk_unit(A5lo, K5, 0, kb);
+  }
+}
+
+// uniform time, backward: tsum[o] += sum over rows of dE[:, TCOL + o]
+__global__ void __launch_bounds__(256) tfeat_colsum_kernel(int Pp, int n_t, const int* __restrict__ tu,
+                                                           const float* __restrict__ dE, float* __restrict__ tsum) {
+  if (!tu[0]) return;
+  __shared__ float s_part[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // a warp reads 32 consecutive time-feature gradients of one row per step (coalesced 128 B)
+  float acc = 0.f;
+  for (int p = blockIdx.x * 8 + wid; p < Pp; p += gridDim.x * 8)
+    if (lane < n_t) acc += dE[(size_t)p * K0 + TCOL + lane];
+  s_part[wid][lane] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_part[w][lane];
+    if (lane < n_t) atomicAdd(&tsum[lane], v);
+  }
+}
+// uniform time, backward: tile 0 of dZt1 = [tsum; 0; 0; ...]
+__global__ void __launch_bounds__(ACT_R) tfeat_row0_kernel(const int* __restrict__ tu, const float* __restrict__ tsum,
+                                                           __nv_bfloat16* __restrict__ dZ) {
+  if (!tu[0]) return;
+  const int p = threadIdx.x;
+  float v[32];
+#pragma unroll
+  for (int o = 0; o < 32; ++o) v[o] = (p == 0) ? tsum[o] : 0.f;
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) *blk_unit(dZ, 32, p, kb) = pack8(v + 8 * kb);
+}
+
 #define CK(call)                      \
   do {                                \
     cudaError_t e_ = (call);          \
@@ -286,15 +358,19 @@ cudaError_t launch_mlp_forward(const DglNet& n, int P, const float* x, const flo
   pe_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(P, Pp, x, t, n.has_timenet, n.has_timenet ? 6 : 10, b.A5, b.T0,
                                              hp ? b.A5lo : nullptr, hp ? b.T0lo : nullptr);
   if (n.has_timenet) {
+    t_uniform_kernel<<<1, 1024, 0, s>>>(P, tiles, t, b.tu, b.tsum);
     LayerArgs g = layer(BlkView{b.T0, (size_t)16 * ACT_R, 0}, 16, (CB)n.Wt0, WID, tiles);
+    g.tiles_dev = b.tu + 1;  // tile 0 only when every row has the same t
     g.bias = n.bt0; g.relu = 1; g.out = b.T1; g.out_tile_stride = (size_t)WID * ACT_R;
     g.mask_out = b.Mt1;
     if (hp) { g.A_lo = b.T0lo; g.B_lo = (CB)n.Wt0lo; g.out_lo = b.T1lo; }
     CK(launch_layer_gemm(g, s));
     g = layer(BlkView{b.T1, (size_t)WID * ACT_R, 0}, WID, (CB)n.Wt1, 32, tiles);  // 30 outputs padded to 32
+    g.tiles_dev = b.tu + 1;
     g.bias = n.bt1; g.out = b.A5; g.out_tile_stride = (size_t)K5 * ACT_R; g.out_kb0 = TCOL / 8;
     if (hp) { g.A_lo = b.T1lo; g.B_lo = (CB)n.Wt1lo; g.out_lo = b.A5lo; }
     CK(launch_layer_gemm(g, s));
+    tfeat_broadcast_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(Pp, b.tu, b.A5, hp ? b.A5lo : nullptr);
   }
   for (int l = 0; l < 8; ++l) {
     const BlkView A = (l == 0 || l == 5) ? b.a5() : b.h(l - 1);
@@ -321,9 +397,10 @@ cudaError_t launch_mlp_forward(const DglNet& n, int P, const float* x, const flo
 
 // weight gradient C[256 (X features), N (Y features)] (+)= X^T Y, or its transpose
 static cudaError_t dw(const BlkView& X, const BlkView& Y, int N, int tiles, float* C, int ld, int transpose,
-                      cudaStream_t s, float* colsum_x = nullptr, float* colsum_y = nullptr) {
+                      cudaStream_t s, float* colsum_x = nullptr, float* colsum_y = nullptr,
+                      const int* tiles_dev = nullptr) {
   DwArgs g = {};
-  g.X = X; g.Y = Y; g.N = N; g.tiles = tiles; g.C = C; g.ld = ld; g.transpose = transpose;
+  g.X = X; g.Y = Y; g.N = N; g.tiles = tiles; g.tiles_dev = tiles_dev; g.C = C; g.ld = ld; g.transpose = transpose;
   g.m_valid = WID; g.n_valid = N;
   g.colsum_x = colsum_x; g.colsum_y = colsum_y;  // bias gradients ride along (no separate column-sum pass)
   return launch_dw_gemm(g, s);
@@ -392,14 +469,20 @@ cudaError_t launch_mlp_backward(const DglNet& n, int P, const float* x, const fl
   }
   if (n.has_timenet) {
     const BlkView vT1{b.T1, HS, 0}, vZt1{b.dZt1, (size_t)32 * ACT_R, 0};
-    tfeat_grad_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(Pp, n.in_t, b.dE, b.dZt1);
-    CK(dw(vT1, vZt1, 32, tiles, gr.dWt1, WID, 1, s, nullptr, gr.dbt1));  // dWt1[32,256] = dZt1^T . T1 (transposed form)
+    // per-row feature gradients, or (uniform time, flag on the device) their column sums in row 0 of tile 0
+    cudaMemsetAsync(b.tsum, 0, 32 * sizeof(float), s);
+    tfeat_grad_kernel<<<(Pp + 255) / 256, 256, 0, s>>>(Pp, n.in_t, b.tu, b.dE, b.dZt1);
+    tfeat_colsum_kernel<<<min(592, (Pp + 7) / 8), 256, 0, s>>>(Pp, n.in_t, b.tu, b.dE, b.tsum);
+    tfeat_row0_kernel<<<1, ACT_R, 0, s>>>(b.tu, b.tsum, b.dZt1);
+    const int* td = b.tu + 1;
+    CK(dw(vT1, vZt1, 32, tiles, gr.dWt1, WID, 1, s, nullptr, gr.dbt1, td));  // dWt1[32,256] = dZt1^T . T1 (transposed form)
     LayerArgs g = layer(vZt1, 32, (CB)n.Wt1T, WID, tiles);
+    g.tiles_dev = td;
     g.mask_bits = b.Mt1;
     g.out = b.dZ[cur ^ 1]; g.out_tile_stride = HS;
     CK(launch_layer_gemm(g, s));
     CK(dw(BlkView{b.dZ[cur ^ 1], HS, 0}, BlkView{b.T0, (size_t)16 * ACT_R, 0}, 16, tiles, gr.dWt0, 16, 0, s,
-          gr.dbt0));
+          gr.dbt0, nullptr, td));
   }
   if (dx) pe_backward_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, x, b.dE, dx);
   return cudaGetLastError();

@@ -42,6 +42,7 @@ struct LayerArgs {
   const __nv_bfloat16* B;     // blocked single tile, R = N rows: [K/8][N][8]
   int K, N;                   // K % 16 == 0, N % 16 == 0, 16 <= N <= 256
   int tiles;                  // 128-row tiles
+  const int* tiles_dev;       // optional: device-side cap on `tiles` (decided by an earlier kernel of the stream)
   int rows_valid;             // rows < rows_valid are written to the fp32 output
   const float* bias;          // [N] or null
   int relu;
@@ -117,7 +118,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) layer_gemm_kernel(const LayerAr
   const int nkb = g.K >> 3;            // 8-wide k blocks
   const int nchunks = (nkb + 7) >> 3;  // K chunks of (up to) 64
   const int npasses = g.A_lo ? 3 : 1;
-  const int my_tiles = (g.tiles > (int)blockIdx.x) ? (g.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_tiles = g.tiles_dev ? min(g.tiles, *g.tiles_dev) : g.tiles;
+  const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ producer
@@ -313,6 +315,7 @@ struct DwArgs {
   BlkView Y;      // rows x N features from Y.kb0
   int N;          // multiple of 16, <= 256
   int tiles;
+  const int* tiles_dev;  // optional device-side cap on `tiles`
   float* C;       // fp32, leading dimension ld
   int ld;
   int transpose;  // 0: C[m, n] (m = X feature, n = Y feature);  1: C[n, m]
@@ -355,7 +358,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const DwArgs g) 
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = s_tmem;
-  const int my_tiles = (g.tiles > (int)blockIdx.x) ? (g.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_tiles = g.tiles_dev ? min(g.tiles, *g.tiles_dev) : g.tiles;
+  const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int m0 = blockIdx.y * 128;  // first X feature of this CTA
 
   if (warp == 0) {

@@ -233,3 +233,43 @@ def test_is_6dof_screw_motion_head_matches_reference(cls):
     moved = ru.from_homogenous(torch.bmm(oa[0].detach(), ru.to_homogenous(p).unsqueeze(-1)).squeeze(-1))
     want = ref.rigid_utils.from_homogenous(torch.bmm(ob[0].detach(), ref.rigid_utils.to_homogenous(p).unsqueeze(-1)).squeeze(-1))
     assert util.rel_l2(moved, want) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [3000, 100, 128, 129])
+def test_uniform_time_shortcut_matches_reference_and_the_general_path(n):
+    """DG-Mesh calls a network with ONE time for all points (train.py:158-172).  The kernels detect that on the
+    device and run the time-net on one tile: outputs must be bit-identical to the general path (made non-uniform
+    by moving the LAST row's t by one ulp), gradients equal to the reference's."""
+    tu = importlib.import_module("utils.time_utils")
+    torch.manual_seed(2)
+    mine = tu.DeformNetworkNormal(is_blender=True).cuda()
+    theirs = ref.time_utils.DeformNetworkNormal(is_blender=True).cuda()
+    theirs.load_state_dict(mine.state_dict())
+    x, _ = inputs(n, 8)
+    x = x.cuda()
+    t = torch.full((n, 1), 0.37, device="cuda")
+    t_general = t.clone()
+    t_general[-1] = torch.nextafter(t_general[-1], torch.tensor([1.0], device="cuda"))
+    xa, xb, xc = (x.clone().requires_grad_(True) for _ in range(3))
+    ya = torch.cat(mine(xa, t), -1)
+    yc = torch.cat(mine(xc, t_general), -1)
+    assert torch.equal(ya[:-1], yc[:-1])                       # same rows, same values, whichever path ran
+    yb = torch.cat(theirs(xb, t), -1)
+    assert util.rel_l2(ya, yb) < 1e-4
+    g = torch.randn(ya.shape, generator=torch.Generator().manual_seed(4)).cuda()
+    ya.backward(g)
+    ga = {k: p.grad.clone() for k, p in mine.named_parameters()}
+    for p in mine.parameters():
+        p.grad = None
+    yc.backward(g)
+    yb.backward(g)
+    pb = dict(theirs.named_parameters())
+    errs = {"dx": util.rel_l2(xa.grad, xb.grad)}
+    for k, v in ga.items():
+        errs[k] = util.rel_l2(v, pb[k].grad)
+    bad = {k: v for k, v in errs.items() if v > 2e-2}
+    assert not bad, bad
+    # the two paths agree with each other far more closely than either does with fp32 (one row's t moved by 1 ulp)
+    for k, p in mine.named_parameters():
+        assert util.rel_l2(ga[k], p.grad) < 5e-3, k

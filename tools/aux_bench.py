@@ -92,5 +92,32 @@ row = {"verts": nv, "faces": nf, "fwd_bwd_ms": timeit(mc_step, steps=5)}
 with torch.no_grad():
     row["fwd_ms"] = timeit(lambda: mc(phi, deform=None, isovalue=0.0), steps=5)
 row["algorithmic_GBps_fwd"] = (4 * G ** 3 + 12 * nv + 12 * nf) / (row["fwd_ms"] * 1e-3) / 1e9
+
+
+def mc_kernels_only():
+    """count + scan + emit + resolve through the C-ABI with fixed capacities and no host wait: the device time
+    of the forward (the API call above adds the host's wait for {V, F} and its allocations)"""
+    import _dgm_lib
+    lib = _dgm_lib.lib()
+    nbytes = _dgm_lib.c_size_t()
+    lib.dgmc_workspace_size(G, nbytes)
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    totals = torch.empty(2, dtype=torch.int32, device=dev)
+    vc, fc = int(nv * 1.25) + 1024, int(nf * 1.25) + 1024
+    v = torch.empty(vc, 3, device=dev)
+    f = torch.empty(fc, 3, dtype=torch.int32, device=dev)
+    g = phi.contiguous().float().reshape(G, G, G)
+    st = _dgm_lib.stream_ptr()
+
+    def run():
+        lib.dgmc_count(G, g.data_ptr(), 0.0, ws.data_ptr(), nbytes.value, totals.data_ptr(), None, None, st)
+        lib.dgmc_emit(G, g.data_ptr(), 0.0, ws.data_ptr(), nbytes.value, v.data_ptr(), vc, f.data_ptr(), fc, st)
+    ms = timeit(run, steps=20)
+    assert totals.tolist() == [nv, nf], (totals.tolist(), nv, nf)
+    return ms
+
+
+row["fwd_kernels_only_ms"] = mc_kernels_only()
+row["algorithmic_GBps_kernels_only"] = (4 * G ** 3 + 12 * nv + 12 * nf) / (row["fwd_kernels_only_ms"] * 1e-3) / 1e9
 out["mc_288"] = row
 print(json.dumps(out))

@@ -164,15 +164,19 @@ __global__ void __launch_bounds__(32 * MC_WARPS) mc_count_kernel(McGeom g, const
   if (lane == 0) blk_counts[brick] = (unsigned long long)(c & 0xffffu) | ((unsigned long long)(c >> 16) << 32);
 }
 
+// {V, F} -> the workspace copy (resolve pass), the caller's device copy and its host-mapped mirror
 __global__ void mc_totals_kernel(size_t nb, const unsigned long long* __restrict__ counts,
-                                 const unsigned long long* __restrict__ offsets, int32_t* __restrict__ totals,
-                                 volatile int32_t* __restrict__ totals_host) {
+                                 const unsigned long long* __restrict__ offsets, int32_t* __restrict__ ws_totals,
+                                 int32_t* __restrict__ totals, volatile int32_t* __restrict__ totals_host) {
   const unsigned long long t = offsets[nb - 1] + counts[nb - 1];
-  totals[0] = (int32_t)(t & 0xffffffffull);
-  totals[1] = (int32_t)(t >> 32);
+  const int32_t V = (int32_t)(t & 0xffffffffull), F = (int32_t)(t >> 32);
+  ws_totals[0] = V;
+  ws_totals[1] = F;
+  totals[0] = V;
+  totals[1] = F;
   if (totals_host) {
-    totals_host[0] = totals[0];
-    totals_host[1] = totals[1];
+    totals_host[0] = V;
+    totals_host[1] = F;
     __threadfence_system();
   }
 }
@@ -326,8 +330,7 @@ cudaError_t launch_mc_count(int G, const float* phi, float iso, void* ws, int32_
   mc_count_kernel<<<(unsigned)((nb + MC_WARPS - 1) / MC_WARPS), 32 * MC_WARPS, 0, s>>>(g, phi, iso, w.blk_counts);
   size_t tb = w.cub_bytes;
   cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, w.blk_counts, w.blk_offsets, (int)nb, s);
-  mc_totals_kernel<<<1, 1, 0, s>>>(nb, w.blk_counts, w.blk_offsets, w.totals, nullptr);
-  mc_totals_kernel<<<1, 1, 0, s>>>(nb, w.blk_counts, w.blk_offsets, totals, (volatile int32_t*)totals_host);
+  mc_totals_kernel<<<1, 1, 0, s>>>(nb, w.blk_counts, w.blk_offsets, w.totals, totals, (volatile int32_t*)totals_host);
   if (ev) cudaEventRecord(ev, s);
   return cudaGetLastError();
 }

@@ -41,7 +41,8 @@ __device__ __forceinline__ void rank_barrier(uint32_t* const* __restrict__ pads,
   __syncthreads();
 }
 
-// per-device grid bookkeeping (one process drives one GPU; the kernel runs on one stream at a time)
+// per-device grid bookkeeping (one process drives one GPU; launches of this kernel must be stream-ordered with
+// respect to each other -- one all-reduce at a time per device; epochs start at 1)
 __device__ unsigned int g_nvls_go;       // epoch of the last start barrier block 0 has passed
 __device__ unsigned int g_nvls_arrived;  // blocks that have finished their slice
 
@@ -104,7 +105,11 @@ __global__ void __launch_bounds__(512) nvls_allreduce_kernel(float* __restrict__
   if (threadIdx.x == 0) s_last = (atomicAdd(&g_nvls_arrived, 1u) == gridDim.x - 1) ? 1u : 0u;
   __syncthreads();
   if (s_last) {
-    if (threadIdx.x == 0) g_nvls_arrived = 0;
+    if (threadIdx.x == 0) {
+      g_nvls_arrived = 0;
+      g_nvls_go = 0;  // every block of this launch is past the start: the next launch (any buffer, any epoch >= 1)
+                      // must not find a stale go value equal to its own epoch
+    }
     rank_barrier(pads, rank, world, epoch + 1);
   }
 }

@@ -37,6 +37,14 @@ def timed(fn, steps=20, warmup=5):
 
 
 out = {"world": world}
+# a first buffer that performs exactly ONE all-reduce (epoch 1): the next buffer also starts at epoch 1 and must
+# not see a stale "go" value from this one
+_p0 = [torch.nn.Parameter(torch.zeros(4096, device=dev))]
+_fg0 = dp.NvlsFlatGrad(_p0)
+_fg0.flat.fill_(float(rank + 1))
+_r0 = _fg0.allreduce(average=False).clone()
+torch.cuda.synchronize()
+assert float((_r0 - world * (world + 1) / 2).abs().max()) == 0.0, "single-call buffer"
 for name, n in (("c2_gaussian_grads", 5_900_000), ("c4_gaussian_plus_mlp_grads", 15_000_000), ("small", 1000)):
     torch.manual_seed(100 + rank)
     params = [torch.nn.Parameter(torch.zeros(n // 2, device=dev)), torch.nn.Parameter(torch.zeros(n - n // 2, device=dev))]

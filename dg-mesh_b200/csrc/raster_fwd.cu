@@ -36,8 +36,8 @@ namespace dgm {
 //                   cycles/op on the busiest tiles, ncu r1a)
 //   tile_scan_kernel  exclusive offsets of every (tile, bucket) block + tile ranges
 //   scatter_kernel  keys into their block (cursor = the offset table itself)
-//   tile_sort_pack_kernel  each block holds a handful of keys: one thread sorts one block;
-//                   a tile whose largest block is long falls back to a full bitonic sort.
+//   tile_sort_pack_kernel  sorts every block on its own (a handful of keys in spread-out scenes, thousands in
+//                   dense ones: insertion / register / warp / CTA regimes per block) and packs the blend records
 #define DEPTH_BUCKETS 256
 
 struct PreOut {

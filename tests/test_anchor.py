@@ -11,10 +11,9 @@ import torch
 import util
 from test_densify import ATTRS, _build, _reference_model_class
 
-pytestmark = pytest.mark.gpu
 
 
-def _sphere(n_lat=40, n_lon=64, radius=0.5):
+def _sphere(n_lat=40, n_lon=64, radius=0.5, device="cuda"):
     th = torch.linspace(0.05, math.pi - 0.05, n_lat)
     ph = torch.linspace(0, 2 * math.pi, n_lon + 1)[:-1]
     T, Ph = torch.meshgrid(th, ph, indexing="ij")
@@ -23,9 +22,10 @@ def _sphere(n_lat=40, n_lon=64, radius=0.5):
     a, b = idx[:-1], idx[1:]
     ar, br = a.roll(-1, 1), b.roll(-1, 1)
     f = torch.cat([torch.stack([a, b, ar], -1).reshape(-1, 3), torch.stack([ar, b, br], -1).reshape(-1, 3)])
-    return v.cuda(), f.cuda()
+    return v.to(device), f.to(device)
 
 
+@pytest.mark.gpu
 def test_nearest_kernel_matches_brute_force():
     import anchor
     g = torch.Generator().manual_seed(0)
@@ -45,6 +45,7 @@ def test_nearest_kernel_matches_brute_force():
         anchor.nearest(torch.zeros(4, 3), torch.zeros(4, 3))         # CPU tensors: no fallback
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("P,bs,increase_bs", [(20000, 256, 1024), (3000, 16, 50)])
 def test_anchor_mesh_equals_reference(P, bs, increase_bs):
     cls = _reference_model_class()
@@ -103,7 +104,7 @@ def test_anchor_mesh_equals_reference(P, bs, increase_bs):
         assert getattr(a, s).shape == getattr(b, s).shape
 
 
-def test_face_geometry_matches_the_trimesh_restatement():
+def test_face_geometry_matches_the_trimesh_restatement_cpu():
     import os
     import sys
     sys.path.insert(0, os.path.join(util.ROOT, "tools"))
@@ -111,7 +112,7 @@ def test_face_geometry_matches_the_trimesh_restatement():
     harness_stubs.install()
     import anchor
     import trimesh                                    # the functional stand-in of tools/harness_stubs.py, or the real one
-    verts, faces = _sphere(12, 20)
+    verts, faces = _sphere(12, 20, device="cpu")
     c, nrm, e = anchor.face_geometry(verts, faces)
     mesh = trimesh.Trimesh(vertices=verts.cpu().numpy(), faces=faces.cpu().numpy())
     assert torch.allclose(c.cpu(), torch.tensor(mesh.triangles_center, dtype=torch.float), atol=1e-7)

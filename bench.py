@@ -11,7 +11,7 @@ means3D + d_xyz_k, scales + d_scaling_k, rotations + d_rotation_k, exactly what
 gaussian_renderer.render() hands the rasterizer (dgmesh/gaussian_renderer/__init__.py:60-86) -- so the
 rasterizer sees per-frame [F,P,.] parameters; opacity and SH are shared.  At N GPUs each rank renders
 8/N of the frames forward+backward and, when N > 1, the canonical-Gaussian gradients are combined with
-ONE NCCL all-reduce over a flat fp32 buffer ("scaling": "strong").
+ONE all-reduce over a flat fp32 buffer -- this library's NVSwitch kernel on >= 4 GPUs, NCCL on 2 -- ("scaling": "strong").
   value         frames/s over the whole job, inputs resident in HBM, through `BatchGaussianRasterizer`
                 (per-frame-parameter frame batch: one call, binning chains overlapped with blend kernels)
   e2e           the same step fed from pinned HOST buffers every step (cameras + 8-bit ground-truth
@@ -100,7 +100,10 @@ class Exchange:
         self.kind, self.handle, self.epoch = "nccl", None, 1
         n_pad = (n + 3) // 4 * 4
         self.buf = None
-        if world > 1 and os.environ.get("DGMESH_B200_EXCHANGE", "nvls") == "nvls":
+        # measured (profiles/r2_nvls_n2.json, r2_nvls_n8.json): on 8 GPUs our kernel beats ncclAllReduce 1.3-1.5x, on 2
+        # GPUs NCCL's direct peer copy moves less data than a multicast round trip and wins (0.066 vs 0.094 ms)
+        default = "nvls" if world >= 4 else "nccl"
+        if world > 1 and os.environ.get("DGMESH_B200_EXCHANGE", default) == "nvls":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 buf = symm_mem.empty(n_pad, dtype=torch.float32, device=device)
@@ -558,7 +561,9 @@ def main():
         "config": {"workload": "BASELINE.json configs[1]: 100k Gaussians, 800x800, SH degree 3, raster fwd+bwd; "
                                "step = 8-frame batch (8 ring cameras), frames sharded over ranks",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "frames_per_step": FRAMES,
-                   "parallelism": f"dp{world} over frames" + (", 1 NCCL all-reduce of grads" if world > 1 else ""),
+                   "parallelism": f"dp{world} over frames" + (
+                       (", 1 all-reduce of grads (" + ("own NVSwitch kernel" if exchange.handle is not None else "NCCL") + ")")
+                       if world > 1 else ""),
                    "scene": "dynamic: frame k renders xyz + d_xyz_k, scales + d_scaling_k, rotations + d_rotation_k",
                    "api": ("BatchGaussianRasterizer (frame batch, per-frame deformed means/scales/rotations)"
                            + (", step replayed as one CUDA graph" if (ours and use_graph) else "")) if ours

@@ -139,10 +139,14 @@ def edge_opposites(tri, n_verts):
     # first of each run of equal keys pairs with its successor
     first = torch.ones_like(ks, dtype=torch.bool)
     first[1:] = ~same
-    pair_a = torch.nonzero(first[:-1] & same).reshape(-1)
+    # position i starts a pair (i, i+1): both ends learn their partner.  Written as two max-scatters over ALL
+    # adjacent positions (-1 where there is no pair) so that no data-dependent size is read back by the host.
+    pair = first[:-1] & same
+    ia, ib = order[:-1], order[1:]
+    none = torch.full_like(ia, -1)
     partner = torch.full((3 * F,), -1, dtype=torch.long, device=t.device)
-    ia, ib = order[pair_a], order[pair_a + 1]
-    partner[ia], partner[ib] = ib, ia
+    partner.scatter_reduce_(0, ia, torch.where(pair, ib, none), reduce="amax")
+    partner.scatter_reduce_(0, ib, torch.where(pair, ia, none), reduce="amax")
     opp = torch.where(partner >= 0, third[partner.clamp_min(0)], torch.full_like(partner, -1))
     return opp.view(F, 3).to(torch.int32).contiguous()
 

@@ -25,8 +25,11 @@ def _blender2opencv(device):
 
 
 def K_to_projection(K, H, W, n=0.001, f=10.0):
-    """nvdiffrast_utils/util.py:484-490 (argument names as there: it is called with (K, height, width))."""
-    fu, fv, cu, cv = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    """nvdiffrast_utils/util.py:484-490 (argument names as there: it is called with (K, height, width)).
+    The four intrinsics are read on the host: a device-resident K costs ONE copy here (the reference's
+    element-wise float() reads are four blocking copies); the result lives where K lived."""
+    k = K.detach().cpu() if K.is_cuda else K
+    fu, fv, cu, cv = float(k[0, 0]), float(k[1, 1]), float(k[0, 2]), float(k[1, 2])
     return torch.tensor([[2 * fu / W, 0, -2 * cu / W + 1, 0], [0, 2 * fv / H, 2 * cv / H - 1, 0],
                          [0, 0, -(f + n) / (f - n), -2 * f * n / (f - n)], [0, 0, -1, 0]],
                         dtype=torch.float32, device=K.device)
@@ -40,7 +43,9 @@ def transform_pos(mtx, pos):
 
 def _raster(glctx, mesh_v_pos, mesh_t_pos_idx, pose, K, resolution):
     proj = K_to_projection(K, resolution[0], resolution[1])
-    v_pos_clip = transform_pos(proj @ pose, mesh_v_pos)
+    # camera matrices that arrive on the host are multiplied there: one small upload, no kernel, no blocking read
+    mtx = (proj.to(pose.device) @ pose).to(mesh_v_pos.device)
+    v_pos_clip = transform_pos(mtx, mesh_v_pos)
     rast_out, _ = dr.rasterize(glctx, v_pos_clip, mesh_t_pos_idx, resolution=resolution)
     topo = dr.edge_opposites(mesh_t_pos_idx, mesh_v_pos.shape[0]) if mesh_t_pos_idx.shape[0] else None
     return v_pos_clip, rast_out, topo
@@ -110,18 +115,20 @@ def mesh_renderer(glctx, gaussians, d_xyz, d_normal, fid, deform_back, appearanc
     vtx_color = appearance.step(mesh_canonical_xyz, time_input)
     if viewpoint_cam is None:
         return verts, faces, vtx_color
-    dev = verts.device
+    # The camera is host data (numpy / python floats): intrinsics, pose and their product are formed on the host
+    # in float32 and uploaded once.  The reference moves them to the GPU first and then inverts two 4x4 matrices
+    # and reads four intrinsics back there -- six blocking round trips in the middle of the mesh branch.
     if viewpoint_cam.K is not None:
-        K = torch.tensor(viewpoint_cam.K).float().to(dev)
+        K = torch.as_tensor(viewpoint_cam.K).detach().float().cpu()
     else:
         import math
         # utils/graphics_utils.fov2focal (:103-104)
         focalx = viewpoint_cam.image_width / (2 * math.tan(viewpoint_cam.FoVx / 2))
         focaly = viewpoint_cam.image_height / (2 * math.tan(viewpoint_cam.FoVy / 2))
         K = torch.tensor([[focalx, 0, viewpoint_cam.image_width / 2], [0, focaly, viewpoint_cam.image_height / 2],
-                          [0, 0, 1]]).float().to(dev)
-    c2w_blender = torch.tensor(viewpoint_cam.orig_transform).to(dev).float()  # blender/OpenGL camera
-    b2cv = _blender2opencv(dev)
+                          [0, 0, 1]]).float()
+    c2w_blender = torch.as_tensor(viewpoint_cam.orig_transform).detach().float().cpu()   # blender/OpenGL camera
+    b2cv = _blender2opencv("cpu")
     c2w_opencv = c2w_blender @ b2cv
     pose = torch.inverse(b2cv) @ torch.inverse(c2w_opencv)                    # = w2c in the blender convention
     res = [viewpoint_cam.image_height, viewpoint_cam.image_width]

@@ -91,8 +91,9 @@ def write_config(path, data_dir, out_dir, a):
                densify_from_iter=a.densify_from, densification_interval=a.densify_every,
                opacity_reset_interval=1_000_000, dpsr_iter=a.dpsr_iter, dpsr_sig=3.0, grid_res=a.grid_res,
                gaussian_ratio=1.2, init_density_threshold=0.0, mask_loss_weight=1.0, mesh_img_loss_weight=1.0,
-               laplacian_loss_weight=1.0, use_anchor=0.0, anchor_iter=1_000_000, anchor_n_1_bs=128,
-               anchor_0_1_bs=128, anchor_search_radius=0.0015, anchor_interval=100, normal_warm_up=a.normal_warm_up)
+               laplacian_loss_weight=1.0, use_anchor=1.0 if a.anchor_iter < 1_000_000 else 0.0,
+               anchor_iter=a.anchor_iter, anchor_n_1_bs=128, anchor_0_1_bs=128, anchor_search_radius=0.0015,
+               anchor_interval=a.anchor_every, normal_warm_up=a.normal_warm_up)
     with open(path, "w") as f:
         yaml.safe_dump(cfg, f)
 
@@ -204,7 +205,8 @@ def run(a):
         torch.Tensor.backward = orig_backward
     out_line = {"stack": a.stack, "iters_done": len(rec["loss"]), "error": err, "wall_s": round(time.time() - t0, 1),
                 "image": [a.size, a.size], "config": {"warm_up": a.warm_up, "dpsr_iter": a.dpsr_iter,
-                                                      "densify_from": a.densify_from, "densify_every": a.densify_every},
+                                                      "densify_from": a.densify_from, "densify_every": a.densify_every,
+                                                      "anchor_iter": a.anchor_iter, "anchor_every": a.anchor_every},
                 "loss": rec["loss"], "img_mean": rec["img_mean"], "n_gauss": rec["n_gauss"],
                 "iter_ms_median_last_half": (float(np.median(rec["iter_ms"][len(rec["iter_ms"]) // 2:]))
                                              if rec["iter_ms"] else None),
@@ -237,6 +239,9 @@ if __name__ == "__main__":
     ap.add_argument("--dpsr-iter", dest="dpsr_iter", type=int, default=1_000_000)
     ap.add_argument("--normal-warm-up", dest="normal_warm_up", type=int, default=10)
     ap.add_argument("--grid-res", dest="grid_res", type=int, default=64)
+    ap.add_argument("--anchor-iter", dest="anchor_iter", type=int, default=1_000_000,
+                    help="first iteration after which anchor_mesh runs (train.py:288-303); default: never")
+    ap.add_argument("--anchor-every", dest="anchor_every", type=int, default=100)
     ap.add_argument("--densify-from", dest="densify_from", type=int, default=20)
     ap.add_argument("--densify-every", dest="densify_every", type=int, default=15)
     ap.add_argument("--work", default=None)

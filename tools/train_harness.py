@@ -87,7 +87,10 @@ def make_dataset(path, n_train=12, n_test=2, size=200, seed=0):
 def write_config(path, data_dir, out_dir, a):
     import yaml
     cfg = dict(source_path=data_dir, model_path=out_dir, downsample=1.0, white_background=True, eval=True,
-               is_blender=True, iterations=1_000_000, warm_up=a.warm_up, densify_until_iter=1_000_000,
+               is_blender=True, iterations=1_000_000, warm_up=a.warm_up,
+               # as in the reference's configs (densify_until_iter 15 000 < anchor_iter 16 000): train.py's
+               # densification bookkeeping (:489-496) indexes with the pre-anchor visibility mask
+               densify_until_iter=min(1_000_000, a.anchor_iter),
                densify_from_iter=a.densify_from, densification_interval=a.densify_every,
                opacity_reset_interval=1_000_000, dpsr_iter=a.dpsr_iter, dpsr_sig=3.0, grid_res=a.grid_res,
                gaussian_ratio=1.2, init_density_threshold=0.0, mask_loss_weight=1.0, mesh_img_loss_weight=1.0,

@@ -276,11 +276,12 @@ class _RasterizeGaussians(torch.autograd.Function):
         base = flat.data_ptr()
         ptrs = [base + 4 * x for x in offs]
 
-        def gview(i, *shape):
-            n = 1
-            for d in shape:
+        def gview(i, *shape):     # one as_strided per gradient (slice + view cost twice as much on the host)
+            stride, n = [], 1
+            for d in reversed(shape):
+                stride.append(n)
                 n *= d
-            return flat[offs[i]:offs[i] + n].view(*shape)
+            return flat.as_strided(shape, stride[::-1], offs[i])
 
         dpix = _f32c(grad_out_color, "grad_out_color")
         p = _dgm_lib.ptr
@@ -452,12 +453,13 @@ class _RasterizeGaussiansBatch(torch.autograd.Function):
         ptrs = [base + 4 * x for x in offs]
 
         def gview(i, bit, *shape):
-            n = 1
-            for d in shape:
-                n *= d
             if bit and (pf & bit):
-                return flat[offs[i]:offs[i] + F * n].view(F, *shape)
-            return flat[offs[i]:offs[i] + n].view(*shape)
+                shape = (F,) + shape
+            stride, n = [], 1
+            for d in reversed(shape):
+                stride.append(n)
+                n *= d
+            return flat.as_strided(shape, stride[::-1], offs[i])
 
         dpix = _f32c(grad_out_color, "grad_out_color")
         p = _dgm_lib.ptr

@@ -60,6 +60,35 @@ def face_geometry(verts, faces):
     return centroids.float(), normals.float(), edge_len
 
 
+def select_topn(face_indices, faces, n_faces, topn):
+    """Which Gaussians of the drawn faces survive to be averaged, and which are deleted.
+
+    face_indices [G] int64: the face every Gaussian is assigned to; faces [X]: the drawn faces (distinct).
+    Returns (to_delete [G] bool, members [X, topn] int64): per drawn face, in the order of `faces`, its first `topn`
+    Gaussians by index; every further Gaussian of a drawn face is marked for deletion.  Same selection as the
+    reference's `[X, G, 1]` match mask + row-wise cumsum (gaussian_model_dpsr_dynamic_anchor.py:787-799), obtained
+    from one stable sort of the drawn faces' Gaussians.  Raises if a drawn face has fewer than `topn` Gaussians
+    (the reference's `masked_select(...).view(-1, topn, .)` fails there too)."""
+    dev = face_indices.device
+    X = faces.shape[0]
+    row_of_face = torch.full((n_faces,), -1, dtype=torch.int64, device=dev)
+    row_of_face[faces] = torch.arange(X, device=dev)
+    row = row_of_face[face_indices]                                     # [G] row in the batch, -1: not drawn
+    member = torch.nonzero(row >= 0).squeeze(1)                         # ascending Gaussian index
+    order = torch.sort(row[member], stable=True).indices               # by row, index order kept inside a row
+    member = member[order]
+    rows_sorted = row[member]
+    per_row = torch.bincount(rows_sorted, minlength=X)
+    first = torch.cumsum(per_row, 0) - per_row
+    rank = torch.arange(member.shape[0], device=dev) - first[rows_sorted]
+    keep = rank < topn
+    if X and int(per_row.min()) < topn:
+        raise RuntimeError("anchor_mesh: a drawn face has fewer than topn Gaussians")
+    to_delete = torch.zeros(face_indices.shape[0], dtype=torch.bool, device=dev)
+    to_delete[member[~keep]] = True
+    return to_delete, member[keep].view(X, topn)
+
+
 def _average_and_prune(self, sel, deform, deform_back, t):
     """`average_and_prune` (:599-649) on an index table sel [X, topn] instead of a [X, G, 1] mask."""
     X, topn = sel.shape
@@ -128,26 +157,10 @@ def anchor_mesh(self, verts, faces, deform, deform_back, t, search_radius=0.0005
     # Gaussian, the others are deleted
     random_indices = torch.randperm(face_indices_n_1.shape[0], device=dev)[:bs]
     face_indices_n_1 = face_indices_n_1[random_indices]
-    X = face_indices_n_1.shape[0]
-    row_of_face = torch.full((n_faces,), -1, dtype=torch.int64, device=dev)
-    row_of_face[face_indices_n_1] = torch.arange(X, device=dev)
-    row = row_of_face[face_indices]                                     # [G] row in the batch, -1: not selected
-    member = torch.nonzero(row >= 0).squeeze(1)                         # ascending Gaussian index
-    order = torch.sort(row[member], stable=True).indices               # by row, index order kept inside a row
-    member = member[order]
-    rows_sorted = row[member]
-    per_row = torch.bincount(rows_sorted, minlength=X)
-    first = torch.cumsum(per_row, 0) - per_row
-    rank = torch.arange(member.shape[0], device=dev) - first[rows_sorted]
-    keep = rank < topn
-    if X and int(per_row.min()) < topn:
-        raise RuntimeError("anchor_mesh: a selected face has fewer than topn Gaussians (the reference's "
-                           "masked_select(...).view(-1, topn, .) fails in the same situation)")
-    to_delete = torch.zeros(face_indices.shape[0], dtype=torch.bool, device=dev)
-    to_delete[member[~keep]] = True
+    to_delete, members = select_topn(face_indices, face_indices_n_1, n_faces, topn)
     self.prune_points(to_delete)
     new_index = torch.cumsum(~to_delete, 0) - 1                          # positions after the prune
-    sel = new_index[member[keep]].view(X, topn)
+    sel = new_index[members]
     new_xyz = _average_and_prune(self, sel, deform, deform_back, t)
     face_xyz = centroids[face_indices_n_1]
     anchor_loss_n_1 = torch.norm(face_xyz - new_xyz, dim=-1).mean()

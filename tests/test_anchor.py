@@ -118,3 +118,37 @@ def test_face_geometry_matches_the_trimesh_restatement_cpu():
     assert torch.allclose(c.cpu(), torch.tensor(mesh.triangles_center, dtype=torch.float), atol=1e-7)
     assert torch.allclose(nrm.cpu(), torch.tensor(mesh.face_normals, dtype=torch.float), atol=1e-6)
     assert abs(float(e) - float(mesh.edges_unique_length.mean())) < 1e-9
+
+
+@pytest.mark.parametrize("topn", [2, 3])
+def test_select_topn_equals_the_match_mask_formulation_cpu(topn):
+    """anchor.select_topn (one stable sort) against the reference's formulation of the same selection
+    (gaussian_model_dpsr_dynamic_anchor.py:787-803): an [X, G] match mask, a row-wise running count, the first
+    `topn` matches of every row kept, the remaining matches deleted -- evaluated here with plain loops."""
+    import anchor
+    g = torch.Generator().manual_seed(3 + topn)
+    n_faces, G = 40, 600
+    face_indices = torch.randint(0, n_faces, (G,), generator=g)
+    counts = torch.bincount(face_indices, minlength=n_faces)
+    eligible = torch.nonzero(counts >= topn).squeeze(1)
+    drawn = eligible[torch.randperm(eligible.shape[0], generator=g)[:7]]          # distinct faces, random order
+    to_delete, members = anchor.select_topn(face_indices, drawn, n_faces, topn)
+    want_delete = torch.zeros(G, dtype=torch.bool)
+    want_members = []
+    for f in drawn.tolist():
+        idx = [i for i in range(G) if int(face_indices[i]) == f]
+        want_members.append(idx[:topn])
+        for i in idx[topn:]:
+            want_delete[i] = True
+    assert torch.equal(to_delete, want_delete)
+    assert members.tolist() == want_members
+    # Gaussians of faces that were not drawn are untouched
+    assert not bool(to_delete[~torch.isin(face_indices, drawn)].any())
+    # a drawn face with too few Gaussians is an error, as in the reference
+    few = torch.nonzero((counts > 0) & (counts < topn)).squeeze(1)
+    if few.numel():
+        with pytest.raises(RuntimeError):
+            anchor.select_topn(face_indices, few[:1], n_faces, topn)
+    # nothing drawn: nothing happens
+    td, mm = anchor.select_topn(face_indices, drawn[:0], n_faces, topn)
+    assert not bool(td.any()) and tuple(mm.shape) == (0, topn)

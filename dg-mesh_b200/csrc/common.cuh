@@ -178,4 +178,16 @@ inline cudaError_t launch_pdl(void (*k)(KArgs...), dim3 grid, dim3 block, size_t
 }
 #endif
 
+// One-time per-DEVICE initialisation (constant / global tables, function attributes are per device: a process
+// that touches a second GPU must repeat them there).  `done` is a bit mask of device ordinals; returns true the
+// first time it is called on the current device.  Not atomic: a benign race repeats an idempotent upload.
+inline bool once_per_device(unsigned long long& done) {
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 0 || d >= 64) return true;
+  if ((done >> d) & 1ull) return false;
+  done |= 1ull << d;
+  return true;
+}
+
 }  // namespace dgm

@@ -25,9 +25,9 @@ namespace dgm {
 
 __constant__ float c_win[11];
 
-static bool g_win_uploaded = false;
+static unsigned long long g_win_uploaded = 0;  // per device
 static cudaError_t upload_window() {
-  if (g_win_uploaded) return cudaSuccess;
+  if (!once_per_device(g_win_uploaded)) return cudaSuccess;
   // loss_utils.gaussian(11, 1.5): exp(-(x - 5)^2 / (2 * 1.5^2)) normalised, float32 like torch.Tensor
   float w[11], sum = 0.f;
   for (int i = 0; i < 11; ++i) {
@@ -36,7 +36,7 @@ static cudaError_t upload_window() {
   }
   for (int i = 0; i < 11; ++i) w[i] /= sum;
   cudaError_t e = cudaMemcpyToSymbol(c_win, w, sizeof(w));
-  g_win_uploaded = (e == cudaSuccess);
+  if (e != cudaSuccess) g_win_uploaded = 0;  // retry on the next call
   return e;
 }
 

@@ -283,9 +283,9 @@ __global__ void __launch_bounds__(256) mc_backward_kernel(int G, int V, const fl
   atomicAdd(&dphi[nb], -gr * (iso - p0) / (d * d));
 }
 
-static bool g_tables_uploaded = false;
+static unsigned long long g_tables_uploaded = 0;  // per device
 static cudaError_t upload_tables() {
-  if (g_tables_uploaded) return cudaSuccess;
+  if (!once_per_device(g_tables_uploaded)) return cudaSuccess;
   cudaError_t e = cudaMemcpyToSymbol(g_ntri, MC_NTRI, sizeof(MC_NTRI));
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tri, MC_TRI, sizeof(MC_TRI));
   for (int i = 0; i < 12 && e == cudaSuccess; ++i) {  // the closed form must be the generated table
@@ -293,7 +293,7 @@ static cudaError_t upload_tables() {
     const int lo = axis == 0 ? (k << 1) : (axis == 1 ? ((k & 1) | ((k & 2) << 1)) : k);
     if (lo != MC_EDGE_LO[i]) e = cudaErrorInvalidValue;
   }
-  g_tables_uploaded = (e == cudaSuccess);
+  if (e != cudaSuccess) g_tables_uploaded = 0;  // retry on the next call
   return e;
 }
 

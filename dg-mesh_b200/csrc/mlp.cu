@@ -38,11 +38,10 @@ static int sm_count() {
 }
 
 cudaError_t launch_layer_gemm(const LayerArgs& g, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;  // per device
+  if (once_per_device(attr)) {
     cudaFuncSetAttribute(layer_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_SMEM);
     cudaFuncSetAttribute(layer_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LGR_SMEM);
-    attr = true;
   }
   if (g.tiles <= 0) return cudaSuccess;
   // split-precision layers whose weights fit 128 KB keep B_hi in shared memory for the CTA's lifetime (every
@@ -61,11 +60,8 @@ cudaError_t launch_layer_gemm(const LayerArgs& g, cudaStream_t s) {
 
 // X has 256 features (two 128-feature halves -> grid.y = 2)
 cudaError_t launch_dw_gemm(const DwArgs& g, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
-    attr = true;
-  }
+  static unsigned long long attr = 0;  // per device
+  if (once_per_device(attr)) cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
   if (g.tiles <= 0) return cudaSuccess;
   dim3 grid(min(g.tiles, max(1, sm_count() / 2)), 2);
   dw_gemm_kernel<<<grid, DW_THREADS, DW_SMEM, s>>>(g);

@@ -179,3 +179,43 @@ def test_batch_api_glue(stub, monkeypatch):
     with pytest.raises(ValueError, match="share image size"):
         dgr.BatchGaussianRasterizer(mixed)(means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"],
                                            shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+
+
+def test_batch_camera_cache_is_keyed_by_address_and_version(stub, monkeypatch):
+    """The batch call stacks its cameras once per (tensor address, version counter): the same tensors again hit
+    the cache, an in-place update or a fresh tensor does not.  (The GPU twin checks the rendered images.)"""
+    monkeypatch.setattr(dgr, "_sizes", lambda P, W, H, R: (4096, 60 * R + 128, 8192, 4096,
+                                                           (60 * R + 128 + 511) // 512 * 512, 8192))
+    calls = []
+    orig = dgr._stack_settings_uncached
+    monkeypatch.setattr(dgr, "_stack_settings_uncached", lambda s, d: (calls.append(1), orig(s, d))[1])
+    dgr._stacked.clear()
+    sc = synth.gaussian_scene(n=16, seed=4)
+    cams = [synth.look_at_camera(azimuth_deg=30.0 * k, width=32, height=32) for k in range(2)]
+    sets = [synth.raster_settings_for(c, torch.ones(3), settings_cls=dgr.GaussianRasterizationSettings) for c in cams]
+
+    def run(s):
+        with torch.no_grad():
+            dgr.BatchGaussianRasterizer(s)(means3D=sc["means3D"], means2D=None, opacities=sc["opacities"],
+                                           shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+        return [c for c in stub.calls if c[0] == "dgr_forward_batch"][-1][1][16]      # pointer of the stacked views
+
+    p1 = run(sets)
+    p2 = run(sets)
+    assert len(calls) == 1 and p1 == p2                                  # hit
+    cams[0].world_view_transform.mul_(1.0)                               # in-place: version counter moves
+    run(sets)
+    assert len(calls) == 2
+    fresh = [s._replace(viewmatrix=s.viewmatrix.clone()) for s in sets]  # new tensors, same values
+    run(fresh)
+    assert len(calls) == 3
+    # the cache keeps the source tensors alive (their addresses cannot be recycled while an entry is valid)
+    assert all(len(v[1]) == 2 for v in dgr._stacked.values())
+    assert len(dgr._stacked) <= 8
+
+
+def test_nvls_flat_grad_needs_a_process_group():
+    import dp
+    p = [torch.nn.Parameter(torch.zeros(8))]
+    with pytest.raises(RuntimeError, match="process group"):
+        dp.NvlsFlatGrad(p)

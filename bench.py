@@ -117,6 +117,13 @@ class Exchange:
                 self.blocks = 296   # dp.NvlsFlatGrad.BLOCKS
             except Exception as e:  # recorded in the JSON line
                 self.kind = f"nccl (nvls unavailable: {type(e).__name__}: {e})"
+        if world > 1:
+            # every rank must take the same path: if the symmetric-memory set-up failed anywhere, nobody uses it
+            agreed = torch.tensor([1.0 if self.handle is not None else 0.0], device=device)
+            dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+            if float(agreed) == 0.0 and self.handle is not None:
+                self.handle, self.buf = None, None
+                self.kind = "nccl (another rank could not set up symmetric memory)"
         if self.buf is None:
             self.buf = torch.zeros(n_pad, device=device)
         self.flat = self.buf[:n]

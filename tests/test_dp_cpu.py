@@ -93,3 +93,38 @@ def test_flatgrad_survives_zero_grad_set_to_none_and_densification():
     fg.zero()
     (a2.sum()).backward()
     assert float(fg.allreduce().sum()) == 27.0
+
+
+def _exchange_worker(rank, world, port, out, want_nvls):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if want_nvls:
+        os.environ["DGMESH_B200_EXCHANGE"] = "nvls"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    ex = bench.Exchange(1001, torch.device("cpu"), world)      # no symmetric memory on the CPU: must agree on NCCL
+    ex.flat.fill_(rank + 1.0)
+    ex.allreduce()
+    if rank == 0:
+        torch.save((ex.flat.clone(), ex.kind, ex.handle is None), out)
+    dist.destroy_process_group()
+
+
+def test_bench_exchange_falls_back_consistently_on_every_rank(tmp_path):
+    """bench.Exchange: when the NVSwitch path cannot be set up (here: CPU tensors), every rank ends on the library
+    all-reduce -- the choice is agreed across ranks, so no rank can wait in a kernel the others never launch."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    for want_nvls in (False, True):
+        out = str(tmp_path / f"ex{int(want_nvls)}.pt")
+        port = _free_port()
+        procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, out, want_nvls)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=240)
+            assert p.exitcode == 0
+        flat, kind, no_handle = torch.load(out)
+        assert no_handle and kind.startswith("nccl") and torch.all(flat == 3.0)
+        assert ("unavailable" in kind) == want_nvls

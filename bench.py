@@ -689,6 +689,11 @@ def main():
             except Exception as e:
                 fg = dp.FlatGrad(S.params)
                 fg_kind = f"nccl ({type(e).__name__}: {e})"
+            agreed = torch.tensor([1.0 if isinstance(fg, dp.NvlsFlatGrad) else 0.0], device=dev)
+            dist.all_reduce(agreed, op=dist.ReduceOp.MIN)          # same path on every rank
+            if float(agreed) == 0.0 and isinstance(fg, dp.NvlsFlatGrad):
+                fg = dp.FlatGrad(S.params)
+                fg_kind = "nccl (another rank could not set up symmetric memory)"
 
             def dp_step():
                 fg.zero()
